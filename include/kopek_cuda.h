@@ -1,0 +1,124 @@
+/*
+ * kopek_cuda.h -- C ABI of libkopek_cuda.so, the B200 (sm_100a) implementation
+ * of kopek's FFT frequency-analysis path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types,
+ * never throws or unwinds.  Every entry point returns a kopek_status (0 = OK,
+ * < 0 = error) unless stated; the message of the last failure on the calling
+ * thread is available from kopek_last_error().  There is NO CPU fallback: if no
+ * CUDA device is usable the calls fail with KOPEK_ERR_CUDA.
+ *
+ * Reference interfaces replaced (paths relative to /root/reference):
+ *   kopek_fft_c2c_f64   <- pub fn fft(&[Complex<f64>]) -> Vec<Complex<f64>>   src/fft.rs:6-41
+ *   kopek_show(_format) <- pub fn show(label: &str, buf: &[Complex<f64>])       src/fft.rs:43-52
+ *   kopek_stft_*        <- the per-UI-frame caller blocks that marshal f32 samples,
+ *                          call fft and take magnitudes:
+ *                            examples/beep/view.rs:140-158   (norm(), dB in comment :155)
+ *                            examples/graph/player.rs:56-61 + examples/graph/utils.rs:47-63
+ *                            examples/pong/main.rs:192-196  + examples/pong/utils.rs:36-47
+ * Rust binding: rust/kopek-cuda-sys/src/lib.rs; see INTEGRATION.md.
+ */
+#ifndef KOPEK_CUDA_H
+#define KOPEK_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define KOPEK_API __attribute__((visibility("default")))
+#else
+#define KOPEK_API
+#endif
+
+typedef int32_t kopek_status;
+enum {
+    KOPEK_OK = 0,
+    KOPEK_ERR_INVALID = -1,     /* bad argument (null pointer, size, enum value, alignment) */
+    KOPEK_ERR_CUDA = -2,        /* a CUDA runtime call failed; see kopek_last_error()       */
+    KOPEK_ERR_NOMEM = -3,       /* host or device allocation failed                         */
+    KOPEK_ERR_UNSUPPORTED = -4  /* valid request this build has no kernel for               */
+};
+
+enum { KOPEK_WINDOW_RECT = 0, KOPEK_WINDOW_HANN = 1, KOPEK_WINDOW_HAMMING = 2, KOPEK_WINDOW_CUSTOM = 3 };
+/* What the fused epilogue writes per bin.  COMPLEX: interleaved (re,im) f32,
+ * one output element = 8 bytes; all others: one f32 per bin.
+ * MAG = |X| (norm(), beep/view.rs:155; equals the f32 sqrt-of-squares of
+ * graph/utils.rs:53 up to rounding); POWER = |X|^2; DB = 20*log10|X|. */
+enum { KOPEK_OUT_COMPLEX = 0, KOPEK_OUT_MAG = 1, KOPEK_OUT_POWER = 2, KOPEK_OUT_DB = 3 };
+/* HALF: bins 0..n/2 (n/2+1 per frame, real input makes the rest redundant);
+ * FULL: all n bins, as the reference's callers see them (graph/utils.rs:50 iterates all). */
+enum { KOPEK_BINS_HALF = 0, KOPEK_BINS_FULL = 1 };
+
+/* Thread-local, NUL-terminated, valid until the next failing call on this thread. */
+KOPEK_API const char *kopek_last_error(void);
+KOPEK_API const char *kopek_version(void);
+/* Number of visible CUDA devices (0 if none / driver missing). */
+KOPEK_API int32_t kopek_device_count(void);
+
+/* ---- 1. exact drop-in for kopek::fft::fft (src/fft.rs:6) --------------------
+ * Host pointers, interleaved (re,im) f64 -- the memory layout of &[Complex<f64>].
+ * Output length is kopek_next_pow2(n_in) (usize::next_power_of_two: 0 -> 1); the
+ * input is zero-padded to it (src/fft.rs:31-36).  n_out must equal that length.
+ * The device kernel performs the same radix-2 decimation-in-time butterflies
+ * with the same twiddles, products and sums as src/fft.rs:23-27 without fused
+ * multiply-add, so the result is bit-identical to the f64 recursion. */
+KOPEK_API size_t kopek_next_pow2(size_t n);
+KOPEK_API kopek_status kopek_fft_c2c_f64(const double *in, size_t n_in, double *out, size_t n_out);
+/* `batch` independent transforms of n_in points each, laid out back to back
+ * (input stride n_in, output stride kopek_next_pow2(n_in) complex values). */
+KOPEK_API kopek_status kopek_fft_c2c_f64_batched(const double *in, size_t n_in, size_t batch, double *out);
+/* Same, device-resident buffers, asynchronous on `cuda_stream` (a cudaStream_t; NULL = default). */
+KOPEK_API kopek_status kopek_fft_c2c_f64_device(const double *d_in, size_t n_in, size_t batch, double *d_out,
+                                                int device, void *cuda_stream);
+
+/* kopek::fft::show (src/fft.rs:43-52): label line, then "{:.4}{:+.4}i" bins joined by ", ".
+ * kopek_show_format writes at most cap-1 bytes + NUL into dst and returns the length needed
+ * (snprintf convention; dst may be NULL when cap == 0).  kopek_show prints it to stdout. */
+KOPEK_API size_t kopek_show_format(const char *label, const double *buf, size_t n, char *dst, size_t cap);
+KOPEK_API kopek_status kopek_show(const char *label, const double *buf, size_t n);
+
+/* ---- 2. throughput path: window -> real FFT -> epilogue, one kernel ----------
+ * Frame f covers samples [f*hop, f*hop + n); frames = 1 + (n_samples - n)/hop
+ * (0 if n_samples < n; no edge padding).  n is a power of two in [256, 4096].
+ * Output row f starts at element f*out_pitch_elems (pitch >= bins per frame;
+ * 0 = tightly packed).  Windows are periodic (DFT-even), built in f64, rounded
+ * once to f32: hann w[i] = 0.5-0.5cos(2 pi i/n), hamming 0.54-0.46cos(2 pi i/n). */
+typedef struct kopek_plan kopek_plan;
+KOPEK_API kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint32_t window,
+                                         uint32_t output, uint32_t bins, uint64_t out_pitch_elems, int device);
+/* Replace the window by n caller-supplied f32 coefficients (host pointer). */
+KOPEK_API kopek_status kopek_plan_set_window(kopek_plan *plan, const float *window_host);
+KOPEK_API kopek_status kopek_plan_destroy(kopek_plan *plan);
+KOPEK_API uint64_t kopek_plan_frames(const kopek_plan *plan, uint64_t n_samples);
+KOPEK_API uint64_t kopek_plan_bins(const kopek_plan *plan);          /* per frame                */
+KOPEK_API uint64_t kopek_plan_out_pitch(const kopek_plan *plan);     /* elements between rows    */
+KOPEK_API uint64_t kopek_plan_out_elem_bytes(const kopek_plan *plan);/* 4, or 8 for COMPLEX      */
+KOPEK_API uint32_t kopek_plan_last_launches(const kopek_plan *plan); /* kernels of the last exec */
+
+/* Device-resident execute, asynchronous on cuda_stream.  d_samples: n_samples f32
+ * on the plan's device; d_out: frames*pitch elements.  *n_frames_out (may be NULL)
+ * receives the frame count. */
+KOPEK_API kopek_status kopek_stft_exec(const kopek_plan *plan, const float *d_samples, uint64_t n_samples,
+                                       void *d_out, uint64_t *n_frames_out, void *cuda_stream);
+/* Host-buffer execute (the call a reference-side caller makes): copies chunks of
+ * samples to the device, transforms, copies spectra back, overlapping the three on
+ * internal streams; returns when h_out is complete.  Pinned buffers
+ * (kopek_host_alloc) make the copies asynchronous; pageable memory also works. */
+KOPEK_API kopek_status kopek_stft_exec_host(kopek_plan *plan, const float *h_samples, uint64_t n_samples,
+                                            void *h_out, uint64_t *n_frames_out);
+KOPEK_API kopek_status kopek_host_alloc(void **ptr, size_t bytes);   /* page-locked host memory */
+KOPEK_API kopek_status kopek_host_free(void *ptr);
+
+/* ---- 3. large single transform (four-step), device-resident c2c f32 ----------
+ * n a power of two, 2^13 <= n <= 2^27; natural-order output; d_in != d_out. */
+KOPEK_API kopek_status kopek_fft_large_c2c_f32(const float *d_in, float *d_out, uint64_t n, int device,
+                                               void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KOPEK_CUDA_H */

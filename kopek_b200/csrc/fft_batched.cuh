@@ -1,0 +1,275 @@
+// K1 -- batched real-input FFT with fused window and magnitude/dB epilogue (sm_100a).
+//
+// Replaces, for many frames at once, the caller blocks of the reference that
+// widen f32 samples, call kopek::fft::fft (src/fft.rs:6-41) and take bin
+// magnitudes (examples/beep/view.rs:140-158, examples/graph/utils.rs:47-63,
+// examples/pong/utils.rs:36-47).  One HBM pass in (f32 samples), one out.
+//
+// Algorithm per frame of N real samples (M = N/2):
+//   z[m] = w[2m] x[2m] + i w[2m+1] x[2m+1]           (window fused into the load)
+//   Z    = FFT_M(z)   Stockham autosort, radix 4/8/16 butterflies in registers,
+//                     stages exchanged through XOR-swizzled shared memory
+//   X[k], X[M-k] from Z[k], conj Z[M-k]               (real-input split post-pass)
+//   epilogue: complex | |X| | |X|^2 | 20 log10 |X|    written straight to HBM
+// Each frame is owned by T = M/16 threads holding 16 complex values each.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace kopek {
+
+enum : int { OUT_COMPLEX = 0, OUT_MAG = 1, OUT_POWER = 2, OUT_DB = 3 };
+
+__host__ __device__ __forceinline__ float2 operator+(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ float2 operator-(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float fast_sqrt(float v) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float fast_log2(float v) {
+    float r;
+    asm("lg2.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+// ---- radix butterflies: in place, natural-order output --------------------
+__host__ __device__ __forceinline__ void dft4(float2 &v0, float2 &v1, float2 &v2, float2 &v3) {
+    float2 s0 = v0 + v2, d0 = v0 - v2, s1 = v1 + v3, d1 = v1 - v3;
+    v0 = s0 + s1;
+    v2 = s0 - s1;
+    v1 = make_float2(d0.x + d1.y, d0.y - d1.x);  // d0 - i d1
+    v3 = make_float2(d0.x - d1.y, d0.y + d1.x);  // d0 + i d1
+}
+
+template <int R> struct Dft;
+template <> struct Dft<4> {
+    __host__ __device__ __forceinline__ static void run(float2 *v) { dft4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct Dft<8> {
+    __host__ __device__ __forceinline__ static void run(float2 *v) {
+        constexpr float h = 0.70710678118654752440f;
+        float2 a0 = v[0] + v[4], a1 = v[1] + v[5], a2 = v[2] + v[6], a3 = v[3] + v[7];
+        float2 b0 = v[0] - v[4], t1 = v[1] - v[5], t2 = v[2] - v[6], t3 = v[3] - v[7];
+        float2 b1 = make_float2((t1.x + t1.y) * h, (t1.y - t1.x) * h);   // * W8^1
+        float2 b2 = make_float2(t2.y, -t2.x);                            // * W8^2 = -i
+        float2 b3 = make_float2((t3.y - t3.x) * h, -(t3.x + t3.y) * h);  // * W8^3
+        dft4(a0, a1, a2, a3);
+        dft4(b0, b1, b2, b3);
+        v[0] = a0; v[1] = b0; v[2] = a1; v[3] = b1; v[4] = a2; v[5] = b2; v[6] = a3; v[7] = b3;
+    }
+};
+template <> struct Dft<16> {
+    __host__ __device__ __forceinline__ static void run(float2 *v) {
+        constexpr float h = 0.70710678118654752440f, c = 0.92387953251128675613f, s = 0.38268343236508977173f;
+#pragma unroll
+        for (int t0 = 0; t0 < 4; ++t0) dft4(v[t0], v[t0 + 4], v[t0 + 8], v[t0 + 12]);
+        // v[t0 + 4 k1] *= W16^(t0 k1)
+        v[5] = cmul(v[5], make_float2(c, -s));                        // W16^1
+        v[9] = make_float2((v[9].x + v[9].y) * h, (v[9].y - v[9].x) * h);  // W16^2
+        v[13] = cmul(v[13], make_float2(s, -c));                      // W16^3
+        v[6] = make_float2((v[6].x + v[6].y) * h, (v[6].y - v[6].x) * h);  // W16^2
+        v[10] = make_float2(v[10].y, -v[10].x);                       // W16^4 = -i
+        v[14] = make_float2((v[14].y - v[14].x) * h, -(v[14].x + v[14].y) * h);  // W16^6
+        v[7] = cmul(v[7], make_float2(s, -c));                        // W16^3
+        v[11] = make_float2((v[11].y - v[11].x) * h, -(v[11].x + v[11].y) * h);  // W16^6
+        v[15] = cmul(v[15], make_float2(-c, s));                      // W16^9
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) dft4(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+        // u[k1 + 4 k0] = v[4 k1 + k0]: transpose the 4x4 register tile
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = a + 1; b < 4; ++b) {
+                float2 t = v[4 * a + b];
+                v[4 * a + b] = v[4 * b + a];
+                v[4 * b + a] = t;
+            }
+    }
+};
+
+// ---- per-size configuration -------------------------------------------------
+template <int N_> struct K1Cfg;
+template <> struct K1Cfg<256>  { static constexpr int S = 2, R0 = 8,  R1 = 16, R2 = 1;  static constexpr int SWZ_SHIFT = 4; };
+template <> struct K1Cfg<512>  { static constexpr int S = 2, R0 = 16, R1 = 16, R2 = 1;  static constexpr int SWZ_SHIFT = 4; };
+template <> struct K1Cfg<1024> { static constexpr int S = 3, R0 = 8,  R1 = 8,  R2 = 8;  static constexpr int SWZ_SHIFT = 3; };
+template <> struct K1Cfg<2048> { static constexpr int S = 3, R0 = 4,  R1 = 16, R2 = 16; static constexpr int SWZ_SHIFT = 4; };
+template <> struct K1Cfg<4096> { static constexpr int S = 3, R0 = 8,  R1 = 16, R2 = 16; static constexpr int SWZ_SHIFT = 4; };
+
+template <int N_> struct K1Geom {
+    using C = K1Cfg<N_>;
+    static constexpr int N = N_, M = N_ / 2, R = 16, T = M / R;
+    static constexpr int BLOCK = T >= 128 ? T : 128;       // threads per CTA
+    static constexpr int FPB = BLOCK / T;                  // frames per CTA per iteration
+    static constexpr int PW = M / 2 + 2;                   // post twiddles (padded to even)
+    // shared memory (bytes): stage twiddles, post twiddles, window, exchange buffers
+    static constexpr size_t SMEM = sizeof(float2) * (M + PW + FPB * M) + sizeof(float) * N;
+    __host__ __device__ static constexpr int swz(int q) { return q ^ ((q >> C::SWZ_SHIFT) & 15); }
+};
+
+struct K1Params {
+    const float *x;        // samples
+    void *out;             // spectra
+    const float *win;      // N window coefficients, pre-scaled by 0.5 (nullptr: rectangular)
+    const float2 *tw;      // W_M^e = exp(-2 pi i e / M), e < M
+    const float2 *pw;      // -i W_N^k = (-sin, -cos)(2 pi k / N), k <= M/2
+    uint64_t n_frames;
+    uint64_t hop;
+    uint64_t pitch;        // output elements between rows
+    int full;              // 1: also write the conjugate-symmetric bins M+1..N-1
+    int vec;               // 1: 8-byte sample loads allowed (hop even, base 8-byte aligned)
+};
+
+template <int OUT, bool WIN>
+__device__ __forceinline__ void emit(void *out, uint64_t idx, float2 X) {
+    // X is 2x the spectrum when no window was applied (the 0.5 lives in the window table)
+    if constexpr (OUT == OUT_COMPLEX) {
+        constexpr float sc = WIN ? 1.0f : 0.5f;
+        reinterpret_cast<float2 *>(out)[idx] = make_float2(X.x * sc, X.y * sc);
+    } else {
+        float p = X.x * X.x + X.y * X.y;
+        float r;
+        if constexpr (OUT == OUT_MAG) r = WIN ? fast_sqrt(p) : 0.5f * fast_sqrt(p);
+        else if constexpr (OUT == OUT_POWER) r = WIN ? p : 0.25f * p;
+        else r = fmaf(fast_log2(p), 3.01029995663981195f, WIN ? 0.0f : -6.02059991327962390f);
+        reinterpret_cast<float *>(out)[idx] = r;
+    }
+}
+
+template <int RAD, int NS, int M, int T, class G>
+__device__ __forceinline__ void stage_write(float2 *buf, const float2 *d, int tid) {
+    constexpr int NB = 16 / RAD;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        int j = tid + T * i;
+        int kk = j & (NS - 1);
+        int base = (j - kk) * RAD + kk;
+#pragma unroll
+        for (int k = 0; k < RAD; ++k) buf[G::swz(base + k * NS)] = d[i * RAD + k];
+    }
+}
+
+template <int RAD, int NS, int M, int T, class G>
+__device__ __forceinline__ void stage_read_twiddle(const float2 *buf, const float2 *tw, float2 *d, int tid) {
+    constexpr int NB = 16 / RAD;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        int j = tid + T * i;
+        int kk = j & (NS - 1);
+#pragma unroll
+        for (int t = 0; t < RAD; ++t) {
+            float2 v = buf[G::swz(j + t * (M / RAD))];
+            if (t > 0) v = cmul(v, tw[kk * t * (M / (NS * RAD))]);
+            d[i * RAD + t] = v;
+        }
+    }
+}
+
+template <int RAD> __device__ __forceinline__ void stage_dft(float2 *d) {
+#pragma unroll
+    for (int i = 0; i < 16 / RAD; ++i) Dft<RAD>::run(d + i * RAD);
+}
+
+template <int T> __device__ __forceinline__ void frame_sync() {
+    if constexpr (T <= 32) __syncwarp();
+    else __syncthreads();
+}
+
+template <int N_, int OUT, bool WIN>
+__global__ void __launch_bounds__(K1Geom<N_>::BLOCK)
+k1_stft_kernel(const K1Params p) {
+    using G = K1Geom<N_>;
+    using C = K1Cfg<N_>;
+    constexpr int M = G::M, T = G::T, R0 = C::R0, R1 = C::R1, R2 = C::R2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *s_tw = reinterpret_cast<float2 *>(smem_raw);
+    float2 *s_pw = s_tw + M;
+    float2 *s_ex = s_pw + G::PW;
+    float *s_win = reinterpret_cast<float *>(s_ex + G::FPB * M);
+
+    for (int i = threadIdx.x; i < M; i += G::BLOCK) s_tw[i] = p.tw[i];
+    for (int i = threadIdx.x; i <= M / 2; i += G::BLOCK) s_pw[i] = p.pw[i];
+    if constexpr (WIN)
+        for (int i = threadIdx.x; i < N_; i += G::BLOCK) s_win[i] = p.win[i];
+    __syncthreads();
+
+    const int tid = threadIdx.x % T;
+    const int fslot = threadIdx.x / T;
+    float2 *buf = s_ex + fslot * M;
+    const uint64_t n_groups = (p.n_frames + G::FPB - 1) / G::FPB;
+
+    for (uint64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        uint64_t frame = g * G::FPB + fslot;
+        const bool valid = frame < p.n_frames;
+        if (!valid) frame = p.n_frames - 1;
+        const float *xf = p.x + frame * p.hop;
+
+        float2 d[16];
+        // ---- stage 0: global load (+ window), butterflies over stride M/R0
+#pragma unroll
+        for (int i = 0; i < 16 / R0; ++i) {
+            int j = tid + T * i;
+#pragma unroll
+            for (int t = 0; t < R0; ++t) {
+                int q = j + t * (M / R0);
+                float2 v;
+                if (p.vec) v = __ldg(reinterpret_cast<const float2 *>(xf) + q);
+                else v = make_float2(__ldg(xf + 2 * q), __ldg(xf + 2 * q + 1));
+                if constexpr (WIN) {
+                    float2 w = reinterpret_cast<const float2 *>(s_win)[q];
+                    v.x *= w.x;
+                    v.y *= w.y;
+                }
+                d[i * R0 + t] = v;
+            }
+        }
+        stage_dft<R0>(d);
+        stage_write<R0, 1, M, T, G>(buf, d, tid);
+        frame_sync<T>();
+        // ---- stage 1
+        stage_read_twiddle<R1, R0, M, T, G>(buf, s_tw, d, tid);
+        stage_dft<R1>(d);
+        frame_sync<T>();
+        stage_write<R1, R0, M, T, G>(buf, d, tid);
+        frame_sync<T>();
+        // ---- stage 2
+        if constexpr (R2 > 1) {
+            stage_read_twiddle<R2, R0 * R1, M, T, G>(buf, s_tw, d, tid);
+            stage_dft<R2>(d);
+            frame_sync<T>();
+            stage_write<R2, R0 * R1, M, T, G>(buf, d, tid);
+            frame_sync<T>();
+        }
+        // ---- real-input split + epilogue.  Pair (k, M-k):
+        //   S = Z[k] + conj Z[M-k], D = Z[k] - conj Z[M-k], Q = (-i W_N^k) D
+        //   2 X[k] = S + Q,  2 X[M-k] = conj(S - Q)      (k = 0 gives X[0] and X[M])
+        const uint64_t row = frame * p.pitch;
+#pragma unroll
+        for (int i = 0; i <= 8; ++i) {
+            int k = tid + T * i;
+            if (i == 8 && tid != 0) break;       // the lone k = M/2 pair
+            float2 a = buf[G::swz(k)];
+            float2 b = buf[G::swz((M - k) & (M - 1))];
+            float2 S = make_float2(a.x + b.x, a.y - b.y);
+            float2 D = make_float2(a.x - b.x, a.y + b.y);
+            float2 Q = cmul(D, s_pw[k]);
+            float2 Xk = S + Q;
+            float2 Xm = make_float2(S.x - Q.x, -(S.y - Q.y));
+            if (valid) {
+                emit<OUT, WIN>(p.out, row + k, Xk);
+                if (i < 8) emit<OUT, WIN>(p.out, row + (M - k), Xm);
+                if (p.full) {
+                    // X[N-k] = conj X[k]
+                    if (k > 0) emit<OUT, WIN>(p.out, row + (N_ - k), make_float2(Xk.x, -Xk.y));
+                    if (i < 8 && k > 0) emit<OUT, WIN>(p.out, row + (M + k), make_float2(Xm.x, -Xm.y));
+                }
+            }
+        }
+        frame_sync<T>();
+    }
+}
+
+}  // namespace kopek

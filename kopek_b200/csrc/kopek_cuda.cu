@@ -1,0 +1,573 @@
+// libkopek_cuda.so -- implementation of the C ABI in include/kopek_cuda.h.
+// Host-side plan/stream management around the sm_100a kernels K1 (fft_batched.cuh)
+// and K2 (fft_c2c_f64.cuh).  No CPU compute path exists here: without a CUDA
+// device every call fails with KOPEK_ERR_CUDA.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "fft_c2c_f64.cuh"
+#include "k1_launch.cuh"
+
+namespace kopek {
+
+// ---------------------------------------------------------------- errors ----
+char *err_buf() {
+    static thread_local char buf[512] = {0};
+    return buf;
+}
+kopek_status fail(kopek_status code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(err_buf(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+static int ilog2(size_t n) {
+    int l = 0;
+    while (((size_t)1 << l) < n) ++l;
+    return l;
+}
+
+// ------------------------------------------------------- K2 host context ----
+// The drop-in fft() is a pure function in the reference (src/fft.rs:6); here it
+// owns a lazily created per-process context (device buffers, pinned staging,
+// one stream, twiddle tables keyed by n) behind a mutex so that any thread may
+// call it, like the original.
+struct TwiddleTable {
+    size_t n = 0;
+    int device = -1;
+    double2 *d = nullptr;
+};
+
+struct K2Context {
+    std::mutex mu;
+    int device = 0;
+    bool init = false;
+    cudaStream_t stream = nullptr;
+    void *pinned = nullptr;
+    size_t pinned_bytes = 0;
+    double2 *d_in = nullptr, *d_out = nullptr;
+    size_t d_in_elems = 0, d_out_elems = 0;
+};
+static K2Context g_k2;
+static std::mutex g_tw_mu;
+static std::vector<TwiddleTable> g_tw_tables;   // small LRU, most recent last
+
+constexpr int K2_CHUNK_LOG_MAX = 12;       // 4096 complex f64 = 64 KiB of shared memory
+constexpr size_t K2_PINNED_MAX = 8u << 20; // staging through pinned memory up to 8 MiB
+
+// tw[j] = exp(-i pi (2j)/n) exactly as src/fft.rs:24 builds it:
+//   im = ((-PI) * (i as f64)) / (n as f64), i = 2j;  w = (cos im, sin im)
+static kopek_status k2_get_twiddles(size_t n, int device, const double2 **out) {
+    std::lock_guard<std::mutex> lk(g_tw_mu);
+    for (size_t t = 0; t < g_tw_tables.size(); ++t)
+        if (g_tw_tables[t].n == n && g_tw_tables[t].device == device) {
+            TwiddleTable hit = g_tw_tables[t];
+            g_tw_tables.erase(g_tw_tables.begin() + t);
+            g_tw_tables.push_back(hit);
+            *out = hit.d;
+            return KOPEK_OK;
+        }
+    size_t cnt = n / 2 ? n / 2 : 1;
+    std::vector<double2> h(cnt);
+    const double fn = (double)n;
+    for (size_t j = 0; j < cnt; ++j) {
+        double fi = (double)(2 * j);
+        double th = (-1.0 * M_PI) * fi / fn;
+        h[j] = make_double2(cos(th), sin(th));
+    }
+    TwiddleTable tb;
+    tb.n = n;
+    tb.device = device;
+    KOPEK_CUDA(cudaMalloc(&tb.d, cnt * sizeof(double2)));
+    cudaError_t e = cudaMemcpy(tb.d, h.data(), cnt * sizeof(double2), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(tb.d);
+        return fail(KOPEK_ERR_CUDA, "twiddle upload failed: %s", cudaGetErrorString(e));
+    }
+    if (g_tw_tables.size() >= 8) {   // evict least recently used
+        // the evicted table may still be read by a kernel in flight on some stream
+        cudaDeviceSynchronize();
+        cudaFree(g_tw_tables.front().d);
+        g_tw_tables.erase(g_tw_tables.begin());
+    }
+    g_tw_tables.push_back(tb);
+    *out = tb.d;
+    return KOPEK_OK;
+}
+
+// Device-resident batched c2c f64.  n = next_pow2(n_in) per transform.
+static kopek_status k2_run_device(const double2 *d_in, size_t n_in, size_t batch, double2 *d_out, int device,
+                                  cudaStream_t stream) {
+    const size_t n = kopek_next_pow2(n_in);
+    if (n > ((size_t)1 << 30)) return fail(KOPEK_ERR_UNSUPPORTED, "fft length %zu exceeds 2^30", n);
+    const int logn = ilog2(n);
+    const double2 *tw = nullptr;
+    kopek_status st = k2_get_twiddles(n, device, &tw);
+    if (st != KOPEK_OK) return st;
+    const int chunk_log = std::min(logn, K2_CHUNK_LOG_MAX);
+    const size_t smem = sizeof(double2) << chunk_log;
+    static bool attr_done = false;
+    if (!attr_done) {
+        KOPEK_CUDA(cudaFuncSetAttribute(k2_c2c_f64_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(sizeof(double2) << K2_CHUNK_LOG_MAX)));
+        attr_done = true;
+    }
+    const size_t chunks = n >> chunk_log;
+    const int threads = (int)std::min<size_t>(1024, std::max<size_t>(32, ((size_t)1 << chunk_log) / 2));
+    for (size_t b0 = 0; b0 < batch; b0 += 65535) {
+        size_t nb = std::min<size_t>(65535, batch - b0);
+        dim3 grid((unsigned)chunks, (unsigned)nb);
+        k2_c2c_f64_chunk<<<grid, threads, smem, stream>>>(d_in + b0 * n_in, n_in, n_in, d_out + b0 * n, n, tw, logn,
+                                                         chunk_log);
+        KOPEK_CUDA(cudaGetLastError());
+        for (int lv = chunk_log + 1; lv <= logn; ++lv)
+            for (size_t b = 0; b < nb; ++b) {
+                size_t nbf = n / 2;
+                k2_c2c_f64_level<<<(unsigned)((nbf + 255) / 256), 256, 0, stream>>>(d_out + (b0 + b) * n, tw, logn, lv);
+                KOPEK_CUDA(cudaGetLastError());
+            }
+    }
+    return KOPEK_OK;
+}
+
+static kopek_status k2_ensure(K2Context &c, size_t in_elems, size_t out_elems, size_t pinned_bytes) {
+    if (!c.init) {
+        const char *env = getenv("KOPEK_DEVICE");
+        c.device = env ? atoi(env) : 0;
+        int cnt = 0;
+        KOPEK_CUDA(cudaGetDeviceCount(&cnt));
+        if (cnt <= 0) return fail(KOPEK_ERR_CUDA, "no CUDA device visible (no CPU fallback exists)");
+        if (c.device < 0 || c.device >= cnt) return fail(KOPEK_ERR_INVALID, "KOPEK_DEVICE=%d out of range", c.device);
+    }
+    DeviceGuard g(c.device);
+    if (!g.ok) return fail(KOPEK_ERR_CUDA, "cannot select device %d", c.device);
+    if (!c.init) {
+        KOPEK_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        c.init = true;
+    }
+    if (in_elems > c.d_in_elems) {
+        if (c.d_in) cudaFree(c.d_in);
+        c.d_in = nullptr; c.d_in_elems = 0;
+        KOPEK_CUDA(cudaMalloc(&c.d_in, in_elems * sizeof(double2)));
+        c.d_in_elems = in_elems;
+    }
+    if (out_elems > c.d_out_elems) {
+        if (c.d_out) cudaFree(c.d_out);
+        c.d_out = nullptr; c.d_out_elems = 0;
+        KOPEK_CUDA(cudaMalloc(&c.d_out, out_elems * sizeof(double2)));
+        c.d_out_elems = out_elems;
+    }
+    if (pinned_bytes > c.pinned_bytes) {
+        if (c.pinned) cudaFreeHost(c.pinned);
+        c.pinned = nullptr; c.pinned_bytes = 0;
+        KOPEK_CUDA(cudaMallocHost(&c.pinned, pinned_bytes));
+        c.pinned_bytes = pinned_bytes;
+    }
+    return KOPEK_OK;
+}
+
+static kopek_status k2_run_host(const double *in, size_t n_in, size_t batch, double *out) {
+    const size_t n = kopek_next_pow2(n_in);
+    if (batch == 0) return KOPEK_OK;
+    if (n_in > 0 && !in) return fail(KOPEK_ERR_INVALID, "in is NULL");
+    if (!out) return fail(KOPEK_ERR_INVALID, "out is NULL");
+    K2Context &c = g_k2;
+    std::lock_guard<std::mutex> lk(c.mu);
+    const size_t in_elems = std::max<size_t>(1, n_in * batch), out_elems = n * batch;
+    const size_t in_bytes = n_in * batch * sizeof(double2), out_bytes = out_elems * sizeof(double2);
+    const bool stage = std::max(in_bytes, out_bytes) <= K2_PINNED_MAX;
+    kopek_status st = k2_ensure(c, in_elems, out_elems, stage ? std::max(in_bytes, out_bytes) : 0);
+    if (st != KOPEK_OK) return st;
+    DeviceGuard g(c.device);
+    if (in_bytes) {
+        if (stage) {
+            memcpy(c.pinned, in, in_bytes);
+            KOPEK_CUDA(cudaMemcpyAsync(c.d_in, c.pinned, in_bytes, cudaMemcpyHostToDevice, c.stream));
+        } else {
+            KOPEK_CUDA(cudaMemcpyAsync(c.d_in, in, in_bytes, cudaMemcpyHostToDevice, c.stream));
+        }
+    }
+    st = k2_run_device(c.d_in, n_in, batch, c.d_out, c.device, c.stream);
+    if (st != KOPEK_OK) return st;
+    KOPEK_CUDA(cudaMemcpyAsync(stage ? c.pinned : (void *)out, c.d_out, out_bytes, cudaMemcpyDeviceToHost, c.stream));
+    KOPEK_CUDA(cudaStreamSynchronize(c.stream));
+    if (stage) memcpy(out, c.pinned, out_bytes);
+    return KOPEK_OK;
+}
+
+// --------------------------------------------------------------- K1 plans ----
+typedef cudaError_t (*k1_launch_fn)(const K1Params &, int, bool, bool, bool, int, cudaStream_t);
+typedef int (*k1_occ_fn)(int, bool);
+typedef K1Info (*k1_info_fn)();
+
+struct HostSlot {            // one in-flight chunk of kopek_stft_exec_host
+    cudaStream_t stream = nullptr;
+    float *d_in = nullptr;
+    void *d_out = nullptr;
+};
+
+}  // namespace kopek
+
+using namespace kopek;
+
+struct kopek_plan {
+    uint32_t n, hop, window, output, bins_mode;
+    uint64_t bins, pitch, elem_bytes;
+    int device;
+    int sm_count, occupancy;
+    K1Info info;
+    k1_launch_fn launch;
+    float *d_win;      // 0.5 * w
+    float2 *d_tw, *d_pw;
+    mutable uint32_t last_launches;
+    // exec_host resources (lazy)
+    std::mutex mu;
+    HostSlot slots[3];
+    uint64_t slot_frames;
+};
+
+namespace kopek {
+
+static void host_window(uint32_t kind, uint32_t n, std::vector<float> &w) {
+    w.resize(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        double c = cos(2.0 * M_PI * (double)i / (double)n);
+        double v = kind == KOPEK_WINDOW_HANN ? 0.5 - 0.5 * c : kind == KOPEK_WINDOW_HAMMING ? 0.54 - 0.46 * c : 1.0;
+        w[i] = (float)v;
+    }
+}
+
+static kopek_status upload_window(kopek_plan *p, const float *w) {
+    // the kernel's window table carries the 1/2 of the real-input split (exact scaling)
+    std::vector<float> half(p->n);
+    for (uint32_t i = 0; i < p->n; ++i) half[i] = 0.5f * w[i];
+    if (!p->d_win) KOPEK_CUDA(cudaMalloc(&p->d_win, p->n * sizeof(float)));
+    KOPEK_CUDA(cudaMemcpy(p->d_win, half.data(), p->n * sizeof(float), cudaMemcpyHostToDevice));
+    return KOPEK_OK;
+}
+
+static void plan_free_device(kopek_plan *p) {
+    if (p->d_win) cudaFree(p->d_win);
+    if (p->d_tw) cudaFree(p->d_tw);
+    if (p->d_pw) cudaFree(p->d_pw);
+    for (HostSlot &s : p->slots) {
+        if (s.d_in) cudaFree(s.d_in);
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+}
+
+}  // namespace kopek
+
+// ================================================================ C ABI =====
+extern "C" {
+
+const char *kopek_last_error(void) { return err_buf(); }
+const char *kopek_version(void) { return "kopek_b200 0.1.0 (sm_100a)"; }
+
+int32_t kopek_device_count(void) {
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return cnt;
+}
+
+size_t kopek_next_pow2(size_t n) {
+    size_t p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+kopek_status kopek_fft_c2c_f64(const double *in, size_t n_in, double *out, size_t n_out) {
+    if (n_out != kopek_next_pow2(n_in))
+        return fail(KOPEK_ERR_INVALID, "n_out=%zu must be next_power_of_two(n_in=%zu)=%zu", n_out, n_in,
+                    kopek_next_pow2(n_in));
+    return k2_run_host(in, n_in, 1, out);
+}
+
+kopek_status kopek_fft_c2c_f64_batched(const double *in, size_t n_in, size_t batch, double *out) {
+    return k2_run_host(in, n_in, batch, out);
+}
+
+kopek_status kopek_fft_c2c_f64_device(const double *d_in, size_t n_in, size_t batch, double *d_out, int device,
+                                      void *cuda_stream) {
+    if (batch == 0) return KOPEK_OK;
+    if ((n_in > 0 && !d_in) || !d_out) return fail(KOPEK_ERR_INVALID, "NULL device pointer");
+    if (d_in == d_out) return fail(KOPEK_ERR_INVALID, "in-place transform is not supported");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(KOPEK_ERR_CUDA, "cannot select device %d", device);
+    return k2_run_device(reinterpret_cast<const double2 *>(d_in), n_in, batch, reinterpret_cast<double2 *>(d_out),
+                         device, (cudaStream_t)cuda_stream);
+}
+
+// "{:.4}{:+.4}i" -- Rust prints NaN unsigned ("NaN"), infinities as "inf"/"-inf"/"+inf".
+static void fmt_bin(std::string &s, double v, bool plus) {
+    char tmp[400];
+    if (v != v) snprintf(tmp, sizeof tmp, "NaN");
+    else snprintf(tmp, sizeof tmp, plus ? "%+.4f" : "%.4f", v);
+    s += tmp;
+}
+size_t kopek_show_format(const char *label, const double *buf, size_t n, char *dst, size_t cap) {
+    std::string s(label ? label : "");
+    s += '\n';
+    for (size_t i = 0; i < n; ++i) {
+        if (i) s += ", ";
+        fmt_bin(s, buf[2 * i], false);
+        fmt_bin(s, buf[2 * i + 1], true);
+        s += 'i';
+    }
+    s += '\n';
+    if (dst && cap) {
+        size_t cp = std::min(cap - 1, s.size());
+        memcpy(dst, s.data(), cp);
+        dst[cp] = 0;
+    }
+    return s.size();
+}
+kopek_status kopek_show(const char *label, const double *buf, size_t n) {
+    if (n && !buf) return fail(KOPEK_ERR_INVALID, "buf is NULL");
+    size_t need = kopek_show_format(label, buf, n, nullptr, 0);
+    std::string s(need + 1, '\0');
+    kopek_show_format(label, buf, n, &s[0], need + 1);
+    fwrite(s.data(), 1, need, stdout);
+    fflush(stdout);
+    return KOPEK_OK;
+}
+
+// ------------------------------------------------------------------ plans ----
+kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint32_t window, uint32_t output,
+                               uint32_t bins, uint64_t out_pitch_elems, int device) {
+    if (!plan) return fail(KOPEK_ERR_INVALID, "plan is NULL");
+    *plan = nullptr;
+    k1_launch_fn launch = nullptr;
+    k1_occ_fn occ = nullptr;
+    k1_info_fn info = nullptr;
+    switch (n) {
+#define KOPEK_CASE(N_) case N_: launch = k1_launch_##N_; occ = k1_occupancy_##N_; info = k1_info_##N_; break;
+        KOPEK_CASE(256) KOPEK_CASE(512) KOPEK_CASE(1024) KOPEK_CASE(2048) KOPEK_CASE(4096)
+#undef KOPEK_CASE
+        default:
+            return fail(KOPEK_ERR_UNSUPPORTED, "frame size %u: must be a power of two in [256, 4096]", n);
+    }
+    if (hop == 0) return fail(KOPEK_ERR_INVALID, "hop must be >= 1");
+    if (window > KOPEK_WINDOW_CUSTOM) return fail(KOPEK_ERR_INVALID, "unknown window %u", window);
+    if (output > KOPEK_OUT_DB) return fail(KOPEK_ERR_INVALID, "unknown output %u", output);
+    if (bins > KOPEK_BINS_FULL) return fail(KOPEK_ERR_INVALID, "unknown bins mode %u", bins);
+    const uint64_t nb = bins == KOPEK_BINS_FULL ? n : n / 2 + 1;
+    if (out_pitch_elems == 0) out_pitch_elems = nb;
+    if (out_pitch_elems < nb) return fail(KOPEK_ERR_INVALID, "out_pitch_elems %llu < bins per frame %llu",
+                                          (unsigned long long)out_pitch_elems, (unsigned long long)nb);
+    int cnt = 0;
+    KOPEK_CUDA(cudaGetDeviceCount(&cnt));
+    if (cnt <= 0) return fail(KOPEK_ERR_CUDA, "no CUDA device visible (no CPU fallback exists)");
+    if (device < 0 || device >= cnt) return fail(KOPEK_ERR_INVALID, "device %d out of range [0,%d)", device, cnt);
+    DeviceGuard g(device);
+    if (!g.ok) return fail(KOPEK_ERR_CUDA, "cannot select device %d", device);
+
+    kopek_plan *p = new (std::nothrow) kopek_plan();
+    if (!p) return fail(KOPEK_ERR_NOMEM, "out of host memory");
+    p->n = n; p->hop = hop; p->window = window; p->output = output; p->bins_mode = bins;
+    p->bins = nb; p->pitch = out_pitch_elems; p->elem_bytes = output == KOPEK_OUT_COMPLEX ? 8 : 4;
+    p->device = device; p->launch = launch; p->info = info();
+    p->d_win = nullptr; p->d_tw = nullptr; p->d_pw = nullptr; p->last_launches = 0; p->slot_frames = 0;
+
+    kopek_status st = KOPEK_OK;
+    do {
+        cudaDeviceProp prop;
+        cudaError_t e = cudaGetDeviceProperties(&prop, device);
+        if (e != cudaSuccess) { st = fail(KOPEK_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); break; }
+        if (prop.major != 10) {
+            st = fail(KOPEK_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library holds sm_100a code only", device,
+                      prop.major, prop.minor);
+            break;
+        }
+        p->sm_count = prop.multiProcessorCount;
+        p->occupancy = occ((int)output, window != KOPEK_WINDOW_RECT);
+        if (p->occupancy <= 0) { st = fail(KOPEK_ERR_CUDA, "kernel for n=%u cannot be resident: %s", n,
+                                           cudaGetErrorString(cudaGetLastError())); break; }
+        const uint32_t M = n / 2;
+        std::vector<float2> tw(M), pw(M / 2 + 1);
+        for (uint32_t e2 = 0; e2 < M; ++e2) {
+            double th = -2.0 * M_PI * (double)e2 / (double)M;
+            tw[e2] = make_float2((float)cos(th), (float)sin(th));
+        }
+        for (uint32_t k = 0; k <= M / 2; ++k) {
+            double th = 2.0 * M_PI * (double)k / (double)n;
+            pw[k] = make_float2((float)-sin(th), (float)-cos(th));
+        }
+        pw[M / 2] = make_float2(-1.0f, 0.0f);   // -i W_N^{N/4} = -1 exactly
+        if ((e = cudaMalloc(&p->d_tw, M * sizeof(float2))) != cudaSuccess ||
+            (e = cudaMalloc(&p->d_pw, (M / 2 + 1) * sizeof(float2))) != cudaSuccess ||
+            (e = cudaMemcpy(p->d_tw, tw.data(), M * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess ||
+            (e = cudaMemcpy(p->d_pw, pw.data(), (M / 2 + 1) * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess) {
+            st = fail(KOPEK_ERR_CUDA, "plan table upload failed: %s", cudaGetErrorString(e));
+            break;
+        }
+        if (window == KOPEK_WINDOW_HANN || window == KOPEK_WINDOW_HAMMING) {
+            std::vector<float> w;
+            host_window(window, n, w);
+            st = upload_window(p, w.data());
+        } else if (window == KOPEK_WINDOW_CUSTOM) {
+            std::vector<float> w(n, 1.0f);   // until kopek_plan_set_window is called
+            st = upload_window(p, w.data());
+        }
+    } while (0);
+    if (st != KOPEK_OK) {
+        plan_free_device(p);
+        delete p;
+        return st;
+    }
+    *plan = p;
+    return KOPEK_OK;
+}
+
+kopek_status kopek_plan_set_window(kopek_plan *plan, const float *window_host) {
+    if (!plan || !window_host) return fail(KOPEK_ERR_INVALID, "NULL argument");
+    if (plan->window != KOPEK_WINDOW_CUSTOM)
+        return fail(KOPEK_ERR_INVALID, "plan was not created with KOPEK_WINDOW_CUSTOM");
+    DeviceGuard g(plan->device);
+    if (!g.ok) return fail(KOPEK_ERR_CUDA, "cannot select device %d", plan->device);
+    KOPEK_CUDA(cudaDeviceSynchronize());
+    return upload_window(plan, window_host);
+}
+
+kopek_status kopek_plan_destroy(kopek_plan *plan) {
+    if (!plan) return KOPEK_OK;
+    DeviceGuard g(plan->device);
+    cudaDeviceSynchronize();
+    plan_free_device(plan);
+    delete plan;
+    return KOPEK_OK;
+}
+
+uint64_t kopek_plan_frames(const kopek_plan *plan, uint64_t n_samples) {
+    if (!plan || n_samples < plan->n) return 0;
+    return 1 + (n_samples - plan->n) / plan->hop;
+}
+uint64_t kopek_plan_bins(const kopek_plan *plan) { return plan ? plan->bins : 0; }
+uint64_t kopek_plan_out_pitch(const kopek_plan *plan) { return plan ? plan->pitch : 0; }
+uint64_t kopek_plan_out_elem_bytes(const kopek_plan *plan) { return plan ? plan->elem_bytes : 0; }
+uint32_t kopek_plan_last_launches(const kopek_plan *plan) { return plan ? plan->last_launches : 0; }
+
+static kopek_status stft_launch(const kopek_plan *plan, const float *d_samples, uint64_t frames, void *d_out,
+                                cudaStream_t stream) {
+    K1Params kp;
+    kp.x = d_samples;
+    kp.out = d_out;
+    kp.win = plan->d_win;
+    kp.tw = plan->d_tw;
+    kp.pw = plan->d_pw;
+    kp.n_frames = frames;
+    kp.hop = plan->hop;
+    kp.pitch = plan->pitch;
+    kp.full = 0;
+    kp.vec = 0;
+    const bool vec = (plan->hop % 2 == 0) && ((uintptr_t)d_samples % 8 == 0);
+    const uint64_t groups = (frames + plan->info.fpb - 1) / plan->info.fpb;
+    const uint64_t resident = (uint64_t)plan->sm_count * plan->occupancy;
+    const int grid = (int)std::min<uint64_t>(groups, resident);
+    cudaError_t e = plan->launch(kp, (int)plan->output, plan->window != KOPEK_WINDOW_RECT,
+                                 plan->bins_mode == KOPEK_BINS_FULL, vec, grid, stream);
+    if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "K1 launch (n=%u) failed: %s", plan->n, cudaGetErrorString(e));
+    return KOPEK_OK;
+}
+
+kopek_status kopek_stft_exec(const kopek_plan *plan, const float *d_samples, uint64_t n_samples, void *d_out,
+                             uint64_t *n_frames_out, void *cuda_stream) {
+    if (!plan) return fail(KOPEK_ERR_INVALID, "plan is NULL");
+    const uint64_t frames = kopek_plan_frames(plan, n_samples);
+    if (n_frames_out) *n_frames_out = frames;
+    plan->last_launches = 0;
+    if (frames == 0) return KOPEK_OK;
+    if (!d_samples || !d_out) return fail(KOPEK_ERR_INVALID, "NULL device pointer");
+    if ((uintptr_t)d_samples % 4 != 0 || (uintptr_t)d_out % plan->elem_bytes != 0)
+        return fail(KOPEK_ERR_INVALID, "misaligned device pointer");
+    DeviceGuard g(plan->device);
+    if (!g.ok) return fail(KOPEK_ERR_CUDA, "cannot select device %d", plan->device);
+    kopek_status st = stft_launch(plan, d_samples, frames, d_out, (cudaStream_t)cuda_stream);
+    if (st == KOPEK_OK) plan->last_launches = 1;
+    return st;
+}
+
+kopek_status kopek_stft_exec_host(kopek_plan *plan, const float *h_samples, uint64_t n_samples, void *h_out,
+                                  uint64_t *n_frames_out) {
+    if (!plan) return fail(KOPEK_ERR_INVALID, "plan is NULL");
+    const uint64_t frames = kopek_plan_frames(plan, n_samples);
+    if (n_frames_out) *n_frames_out = frames;
+    plan->last_launches = 0;
+    if (frames == 0) return KOPEK_OK;
+    if (!h_samples || !h_out) return fail(KOPEK_ERR_INVALID, "NULL host pointer");
+    std::lock_guard<std::mutex> lk(plan->mu);
+    DeviceGuard g(plan->device);
+    if (!g.ok) return fail(KOPEK_ERR_CUDA, "cannot select device %d", plan->device);
+
+    // chunk so that one slot moves ~32 MiB of samples; three slots keep the H2D
+    // engine, the SMs and the D2H engine busy at the same time
+    const uint64_t n = plan->n, hop = plan->hop;
+    uint64_t cf = std::max<uint64_t>(1, ((uint64_t)32 << 20) / (hop * sizeof(float)));
+    cf = std::min(cf, frames);
+    const uint64_t in_elems = (cf - 1) * hop + n;
+    const uint64_t out_bytes = cf * plan->pitch * plan->elem_bytes;
+    if (plan->slot_frames < cf) {
+        for (HostSlot &s : plan->slots) {
+            if (s.d_in) cudaFree(s.d_in);
+            if (s.d_out) cudaFree(s.d_out);
+            s.d_in = nullptr; s.d_out = nullptr;
+            if (!s.stream) KOPEK_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+            KOPEK_CUDA(cudaMalloc(&s.d_in, in_elems * sizeof(float)));
+            KOPEK_CUDA(cudaMalloc(&s.d_out, out_bytes));
+        }
+        plan->slot_frames = cf;
+    }
+    uint32_t launches = 0;
+    uint64_t c = 0;
+    for (uint64_t f0 = 0; f0 < frames; f0 += cf, ++c) {
+        HostSlot &s = plan->slots[c % 3];
+        const uint64_t nf = std::min(cf, frames - f0);
+        const uint64_t ne = (nf - 1) * hop + n;
+        KOPEK_CUDA(cudaMemcpyAsync(s.d_in, h_samples + f0 * hop, ne * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+        kopek_status st = stft_launch(plan, s.d_in, nf, s.d_out, s.stream);
+        if (st != KOPEK_OK) return st;
+        ++launches;
+        // rows are contiguous (pitch) so one copy returns the chunk; the tail of the
+        // last row beyond `bins` is unspecified padding when pitch > bins
+        const uint64_t ob = ((nf - 1) * plan->pitch + plan->bins) * plan->elem_bytes;
+        KOPEK_CUDA(cudaMemcpyAsync((char *)h_out + f0 * plan->pitch * plan->elem_bytes, s.d_out, ob,
+                                   cudaMemcpyDeviceToHost, s.stream));
+    }
+    for (HostSlot &s : plan->slots)
+        if (s.stream) KOPEK_CUDA(cudaStreamSynchronize(s.stream));
+    plan->last_launches = launches;
+    return KOPEK_OK;
+}
+
+kopek_status kopek_host_alloc(void **ptr, size_t bytes) {
+    if (!ptr) return fail(KOPEK_ERR_INVALID, "ptr is NULL");
+    *ptr = nullptr;
+    cudaError_t e = cudaMallocHost(ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) return fail(KOPEK_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return KOPEK_OK;
+}
+kopek_status kopek_host_free(void *ptr) {
+    if (!ptr) return KOPEK_OK;
+    KOPEK_CUDA(cudaFreeHost(ptr));
+    return KOPEK_OK;
+}
+
+kopek_status kopek_fft_large_c2c_f32(const float *, float *, uint64_t, int, void *) {
+    return fail(KOPEK_ERR_UNSUPPORTED, "four-step large transform: not built yet");
+}
+
+}  // extern "C"

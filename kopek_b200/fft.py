@@ -1,0 +1,132 @@
+"""Host-side mirror of the reference's `kopek::fft` module over the C ABI.
+
+Same names, argument meaning and error behaviour as /root/reference/src/fft.rs:
+`fft(input)` takes complex samples and returns the forward DFT zero-padded to
+the next power of two (src/fft.rs:6-41); `show(label, buf)` prints the bins in
+the reference's format (src/fft.rs:43-52).  The reference's `fft` is infallible,
+so any CUDA failure surfaces as an exception (the Rust shim panics) -- there is
+no CPU path to fall back to.
+
+`StftPlan` is the batched throughput path the three callers of `fft`
+(examples/beep/view.rs:140-158, examples/graph/player.rs:56-61,
+examples/pong/main.rs:192-196) map onto when many frames are analysed at once.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import (BINS_FULL, BINS_HALF, OUT_COMPLEX, OUT_DB, OUT_MAG, OUT_POWER, WINDOW_CUSTOM, WINDOW_HAMMING,
+                   WINDOW_HANN, WINDOW_RECT, KopekError, check)
+
+__all__ = ["fft", "fft_batched", "show", "show_format", "StftPlan", "next_pow2", "KopekError",
+           "WINDOW_RECT", "WINDOW_HANN", "WINDOW_HAMMING", "WINDOW_CUSTOM",
+           "OUT_COMPLEX", "OUT_MAG", "OUT_POWER", "OUT_DB", "BINS_HALF", "BINS_FULL"]
+
+
+def next_pow2(n: int) -> int:
+    return int(_lib.load().kopek_next_pow2(n))
+
+
+def fft(input) -> np.ndarray:
+    """kopek::fft::fft -- complex128 in, complex128 out of length next_pow2(len(input)) (>= 1)."""
+    a = np.ascontiguousarray(input, dtype=np.complex128).reshape(-1)
+    out = np.empty(next_pow2(a.size), dtype=np.complex128)
+    check(_lib.load().kopek_fft_c2c_f64(a.ctypes.data if a.size else None, a.size, out.ctypes.data, out.size))
+    return out
+
+
+def fft_batched(frames) -> np.ndarray:
+    """`fft` over each row of a [batch, n_in] complex array in one call."""
+    a = np.ascontiguousarray(frames, dtype=np.complex128)
+    if a.ndim != 2:
+        raise ValueError("frames must be 2-D [batch, n]")
+    out = np.empty((a.shape[0], next_pow2(a.shape[1])), dtype=np.complex128)
+    check(_lib.load().kopek_fft_c2c_f64_batched(a.ctypes.data if a.size else None, a.shape[1], a.shape[0],
+                                                out.ctypes.data))
+    return out
+
+
+def show_format(label: str, buf) -> str:
+    a = np.ascontiguousarray(buf, dtype=np.complex128).reshape(-1)
+    lib = _lib.load()
+    need = lib.kopek_show_format(label.encode(), a.ctypes.data, a.size, None, 0)
+    dst = C.create_string_buffer(need + 1)
+    lib.kopek_show_format(label.encode(), a.ctypes.data, a.size, C.addressof(dst), need + 1)
+    return dst.value.decode()
+
+
+def show(label: str, buf) -> None:
+    """kopek::fft::show -- prints the label line and the "{:.4}{:+.4}i" bins."""
+    a = np.ascontiguousarray(buf, dtype=np.complex128).reshape(-1)
+    check(_lib.load().kopek_show(label.encode(), a.ctypes.data, a.size))
+
+
+class StftPlan:
+    """Fused window -> real FFT -> |X|/dB plan (kopek_plan_* / kopek_stft_exec*)."""
+
+    def __init__(self, n: int, hop: int | None = None, window: int = WINDOW_RECT, output: int = OUT_MAG,
+                 bins: int = BINS_HALF, out_pitch: int = 0, device: int = 0, custom_window=None):
+        self._h = C.c_void_p()
+        self._lib = _lib.load()
+        hop = n if hop is None else hop
+        check(self._lib.kopek_plan_create(C.byref(self._h), n, hop, window, output, bins, out_pitch, device))
+        self.n, self.hop, self.window, self.output, self.device = n, hop, window, output, device
+        self.bins = int(self._lib.kopek_plan_bins(self._h))
+        self.pitch = int(self._lib.kopek_plan_out_pitch(self._h))
+        self.elem_bytes = int(self._lib.kopek_plan_out_elem_bytes(self._h))
+        if custom_window is not None:
+            w = np.ascontiguousarray(custom_window, dtype=np.float32)
+            if w.size != n:
+                raise ValueError("custom window must have n coefficients")
+            check(self._lib.kopek_plan_set_window(self._h, w.ctypes.data))
+
+    def frames(self, n_samples: int) -> int:
+        return int(self._lib.kopek_plan_frames(self._h, n_samples))
+
+    @property
+    def last_launches(self) -> int:
+        return int(self._lib.kopek_plan_last_launches(self._h))
+
+    @property
+    def out_dtype(self):
+        return np.complex64 if self.output == OUT_COMPLEX else np.float32
+
+    def exec_ptr(self, d_samples: int, n_samples: int, d_out: int, stream: int = 0) -> int:
+        """Device pointers in, asynchronous on `stream` (a cudaStream_t as int)."""
+        nf = C.c_uint64(0)
+        check(self._lib.kopek_stft_exec(self._h, d_samples, n_samples, d_out, C.byref(nf), stream or None))
+        return nf.value
+
+    def exec_host_ptr(self, h_samples: int, n_samples: int, h_out: int) -> int:
+        nf = C.c_uint64(0)
+        check(self._lib.kopek_stft_exec_host(self._h, h_samples, n_samples, h_out, C.byref(nf)))
+        return nf.value
+
+    def exec_host(self, samples) -> np.ndarray:
+        """Host numpy samples in, [frames, bins] spectra out (copies inside the call)."""
+        s = np.ascontiguousarray(samples, dtype=np.float32).reshape(-1)
+        frames = self.frames(s.size)
+        out = np.empty((frames, self.pitch), dtype=self.out_dtype)
+        if frames:
+            self.exec_host_ptr(s.ctypes.data, s.size, out.ctypes.data)
+        return out[:, :self.bins]
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.kopek_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

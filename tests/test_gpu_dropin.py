@@ -1,0 +1,86 @@
+"""GPU: the kopek::fft::fft drop-in (kopek_fft_c2c_f64, K2) against the oracle -- bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from util import frame_rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint64)
+
+
+@pytest.mark.parametrize("n_in", [0, 1, 2, 3, 4, 5, 8, 16, 31, 64, 100, 256, 1000, 1024, 2048, 4096, 5000, 8192,
+                                  65536, 100000])
+def test_fft_bit_exact_vs_oracle(built_lib, oracle_mod, n_in):
+    from kopek_b200 import fft
+    rng = np.random.default_rng(1000 + n_in)
+    x = rng.standard_normal(n_in) + 1j * rng.standard_normal(n_in)
+    got = fft.fft(x)
+    ref = oracle_mod.fft(x)
+    assert got.shape == ref.shape == (oracle_mod.next_pow2(n_in),)
+    # same butterflies, same twiddles, no FMA: identical bits (src/fft.rs:23-27)
+    np.testing.assert_array_equal(_bits(got), _bits(ref))
+
+
+def test_fft_config0_sine440(built_lib, oracle_mod):
+    """BASELINE.json configs[0]: 1024-pt spectrum of the 440 Hz / 44.1 kHz Oscillator::sine."""
+    from kopek_b200 import fft
+    g = np.load(os.path.join(GOLDEN, "sine440_1024.npz"))
+    x = oracle_mod.marshal(g["samples"])                 # f32 -> f64 -> Complex{re,0} (pong/main.rs:192-195)
+    got = fft.fft(x)
+    np.testing.assert_array_equal(_bits(got), _bits(oracle_mod.fft(x)))
+    assert frame_rel_err(got, g["spectrum"]) < 4e-15
+    mag = np.abs(got)
+    assert int(mag[:513].argmax()) == 10 and abs(mag.max() - 471.9957) < 1e-3
+    # beep/graph marshalling divides by i16::MAX (beep/view.rs:143)
+    x2 = oracle_mod.marshal(g["samples"], 32767.0)
+    np.testing.assert_array_equal(_bits(fft.fft(x2)), _bits(oracle_mod.fft(x2)))
+
+
+def test_fft_large_and_special_values(built_lib, oracle_mod):
+    from kopek_b200 import fft
+    rng = np.random.default_rng(77)
+    x = rng.standard_normal(1 << 20) + 1j * rng.standard_normal(1 << 20)
+    got = fft.fft(x)
+    np.testing.assert_array_equal(_bits(got), _bits(oracle_mod.fft(x)))
+    assert frame_rel_err(got, np.fft.fft(x)) < 1e-14
+    # impulse -> flat, DC -> bin 0 = N, non-finite input propagates like the reference
+    imp = np.zeros(512, dtype=np.complex128); imp[0] = 1
+    np.testing.assert_array_equal(fft.fft(imp), np.ones(512, dtype=np.complex128))
+    dc = np.ones(512, dtype=np.complex128)
+    y = fft.fft(dc)
+    assert y[0] == 512 and np.abs(y[1:]).max() < 1e-12
+    bad = np.ones(16, dtype=np.complex128); bad[3] = complex(np.inf, 0)
+    np.testing.assert_array_equal(np.isnan(fft.fft(bad)), np.isnan(oracle_mod.fft(bad)))
+
+
+def test_fft_batched_and_device(built_lib, oracle_mod):
+    import torch
+    from kopek_b200 import _lib, fft
+    rng = np.random.default_rng(5)
+    for n_in in (7, 256, 1000):
+        x = rng.standard_normal((33, n_in)) + 1j * rng.standard_normal((33, n_in))
+        got = fft.fft_batched(x)
+        ref = np.stack([oracle_mod.fft(r) for r in x])
+        np.testing.assert_array_equal(_bits(got), _bits(ref))
+    # device-resident entry point on torch's current stream
+    x = rng.standard_normal((1000, 256)) + 1j * rng.standard_normal((1000, 256))
+    d_in = torch.from_numpy(x).cuda()
+    d_out = torch.empty((1000, 256), dtype=torch.complex128, device="cuda")
+    _lib.check(_lib.load().kopek_fft_c2c_f64_device(d_in.data_ptr(), 256, 1000, d_out.data_ptr(), 0,
+                                                    torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = np.stack([oracle_mod.fft(r) for r in x])
+    np.testing.assert_array_equal(_bits(d_out.cpu().numpy()), _bits(ref))
+
+
+def test_show_prints_reference_format(built_lib, capfd):
+    from kopek_b200 import fft
+    fft.show("label", [1 + 2j, -0.5 - 0.25j, 0j, complex(-0.0, -3.14159)])
+    out = capfd.readouterr().out
+    assert out == open(os.path.join(GOLDEN, "show.txt")).read()
