@@ -1,0 +1,190 @@
+// K1W -- warp-per-frame 1024-point real-input FFT + fused window / magnitude epilogue (sm_100a).
+//
+// The headline kernel of the path (BASELINE.json metric: batched 1024-pt FFT+mag).
+// Same mathematics as fft_batched.cuh (K1) -- window, 512-point complex FFT of the
+// packed frame, real-input split, |X| / dB -- but laid out so that ONE WARP owns one
+// frame end to end and the shared-memory data pipe (the measured bottleneck of K1,
+// profiles/r1_v1_k1_full.md: 92 % busy) moves the minimum number of 128-byte wavefronts:
+//
+//   n = 64 n2 + 8 n1 + n0,  k = k2 + 8 k1 + 64 k0          (three radix-8 passes, DIF order)
+//   A: lane (n1, n0 pair) transforms over n2, multiplies by W512^{(8 n1 + n0) k2}
+//   B: lane (k2, n0 pair) transforms over n1 IN PLACE (reads and writes its own slots),
+//      multiplies by W64^{n0 k1}
+//   C: lane (k2, k1 pair) transforms over n0 -> Z[k2 + 8 k1 + 64 k0] in registers
+//   split: the partner Z[M-k] of every bin a lane owns lives in ONE float4 of lane 35-l,
+//      so only the upper half (k0 >= 4) is published and each lane finishes 8 (k, M-k) pairs.
+//
+// All exchanges are 128-bit, conflict free by construction (one spare float4 per eight:
+// slot L sits at L + L/8), and every address is "per-lane base + immediate".
+// tools/k1w_model.py is the numpy model of exactly these address functions.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fft_batched.cuh"
+
+namespace kopek {
+
+struct K1WParams {
+    const float *x;          // samples (16-byte aligned, hop % 4 == 0)
+    void *out;               // spectra
+    const float4 *tables;    // K1W_TABLE_F4 float4: window | TPP | TQ | PW (see k1w_build_tables)
+    uint64_t n_frames;
+    uint64_t hop;
+    uint64_t pitch;
+};
+
+constexpr int K1W_WIN_F4 = 256;            // 0.5 * w[4i .. 4i+3]
+constexpr int K1W_TPP_F4 = 7 * 32;         // [k2-1][lane]  (W256^{lane k2}, W256^{lane k2} W512^{k2})
+constexpr int K1W_TQ_F4 = 7 * 4;           // [k1-1][b]     (W32^{b k1},    W32^{b k1} W64^{k1})
+constexpr int K1W_PW_F4 = 4 * 32;          // [k0][lane]    (-i W1024^{k}, -i W1024^{k+8}), k = k2 + 16 c + 64 k0
+constexpr int K1W_TABLE_F4 = K1W_WIN_F4 + K1W_TPP_F4 + K1W_TQ_F4 + K1W_PW_F4;
+constexpr int K1W_EX_F4 = 288;             // per-warp exchange buffer: 256 slots + 32 spare
+
+template <int WARPS> struct K1WGeom {
+    static constexpr int BLOCK = WARPS * 32;
+    static constexpr size_t SMEM = sizeof(float4) * (K1W_TABLE_F4 + WARPS * K1W_EX_F4);
+};
+
+__device__ __forceinline__ float4 ldg_stream(const float4 *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+template <int OUT, bool WIN, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+k1w_1024_kernel(const K1WParams p) {
+    constexpr int M = 512;
+    extern __shared__ __align__(16) unsigned char k1w_smem[];
+    float4 *s_win = reinterpret_cast<float4 *>(k1w_smem);
+    float4 *s_tpp = s_win + K1W_WIN_F4;
+    float4 *s_tq = s_tpp + K1W_TPP_F4;
+    float4 *s_pw = s_tq + K1W_TQ_F4;
+    float4 *s_ex = s_pw + K1W_PW_F4;
+
+    for (int i = threadIdx.x + (WIN ? 0 : K1W_WIN_F4); i < K1W_TABLE_F4; i += WARPS * 32) s_win[i] = p.tables[i];
+    __syncthreads();
+
+    const int l = threadIdx.x & 31;
+    float4 *ex = s_ex + (threadIdx.x >> 5) * K1W_EX_F4;
+    float4 *exA = ex + l + (l >> 3);                         // + 36 k2
+    float4 *exB = ex + 36 * (l >> 2) + (l & 3);              // + 4 n1 + (n1 >> 1)
+    float4 *exC = ex + 36 * (l >> 2) + 9 * (l & 3);          // + 4 f + s
+    float4 *zW = ex + ((l + 4) & 31);                        // + 32 (k0 - 4)
+    const float4 *zR = ex + (((l >= 4 ? 35 - l : 3 - l) + 4) & 31);   // + 32 (3 - k0)
+    const float4 *tpp = s_tpp + l;                           // + 32 (k2 - 1)
+    const float4 *tq = s_tq + (l & 3);                       // + 4 (k1 - 1)
+    const float4 *pwt = s_pw + l;                            // + 32 k0
+    const float4 *wt = s_win + l;                            // + 32 n2
+    const int kbase = (l >> 2) + 16 * (l & 3);               // k = kbase + 8 f + 64 k0
+
+    const uint64_t total_warps = (uint64_t)gridDim.x * WARPS;
+    for (uint64_t frame = (uint64_t)blockIdx.x * WARPS + (threadIdx.x >> 5); frame < p.n_frames;
+         frame += total_warps) {
+        // ---- A: load + window, transform over n2, twiddle, publish
+        const float4 *xf = reinterpret_cast<const float4 *>(p.x + frame * p.hop) + l;
+        float4 v[8];
+#pragma unroll
+        for (int n2 = 0; n2 < 8; ++n2) v[n2] = ldg_stream(xf + 32 * n2);
+        float2 d0[8], d1[8];
+#pragma unroll
+        for (int n2 = 0; n2 < 8; ++n2) {
+            if constexpr (WIN) {
+                float4 w = wt[32 * n2];
+                d0[n2] = make_float2(v[n2].x * w.x, v[n2].y * w.y);
+                d1[n2] = make_float2(v[n2].z * w.z, v[n2].w * w.w);
+            } else {
+                d0[n2] = make_float2(v[n2].x, v[n2].y);
+                d1[n2] = make_float2(v[n2].z, v[n2].w);
+            }
+        }
+        Dft<8>::run(d0);
+        Dft<8>::run(d1);
+        exA[0] = make_float4(d0[0].x, d0[0].y, d1[0].x, d1[0].y);
+#pragma unroll
+        for (int k2 = 1; k2 < 8; ++k2) {
+            float4 t = tpp[32 * (k2 - 1)];
+            float2 a = cmul(d0[k2], make_float2(t.x, t.y));
+            float2 b = cmul(d1[k2], make_float2(t.z, t.w));
+            exA[36 * k2] = make_float4(a.x, a.y, b.x, b.y);
+        }
+        __syncwarp();
+        // ---- B: in place over n1
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) {
+            float4 t = exB[4 * n1 + (n1 >> 1)];
+            d0[n1] = make_float2(t.x, t.y);
+            d1[n1] = make_float2(t.z, t.w);
+        }
+        Dft<8>::run(d0);
+        Dft<8>::run(d1);
+        exB[0] = make_float4(d0[0].x, d0[0].y, d1[0].x, d1[0].y);
+#pragma unroll
+        for (int k1 = 1; k1 < 8; ++k1) {
+            float4 t = tq[4 * (k1 - 1)];
+            float2 a = cmul(d0[k1], make_float2(t.x, t.y));
+            float2 b = cmul(d1[k1], make_float2(t.z, t.w));
+            exB[4 * k1 + (k1 >> 1)] = make_float4(a.x, a.y, b.x, b.y);
+        }
+        __syncwarp();
+        // ---- C: over n0 -> Z[kbase + 8 f + 64 k0] (d0: f = 0, d1: f = 1)
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            float4 t = exC[s];
+            d0[2 * s] = make_float2(t.x, t.y);
+            d0[2 * s + 1] = make_float2(t.z, t.w);
+            float4 u = exC[4 + s];
+            d1[2 * s] = make_float2(u.x, u.y);
+            d1[2 * s + 1] = make_float2(u.z, u.w);
+        }
+        Dft<8>::run(d0);
+        Dft<8>::run(d1);
+        __syncwarp();
+        // ---- split: publish the upper half, finish the pairs (k, M-k) for k0 < 4
+#pragma unroll
+        for (int k0 = 4; k0 < 8; ++k0) zW[32 * (k0 - 4)] = make_float4(d0[k0].x, d0[k0].y, d1[k0].x, d1[k0].y);
+        __syncwarp();
+        float2 b0[4], b1[4];      // partners Z[M-k] of the f = 0 / f = 1 bins
+#pragma unroll
+        for (int k0 = 0; k0 < 4; ++k0) {
+            float4 t = zR[32 * (3 - k0)];
+            b0[k0] = make_float2(t.z, t.w);
+            b1[k0] = l >= 4 ? make_float2(t.x, t.y) : make_float2(t.z, t.w);
+        }
+        if (l < 4) {              // k2 = 0 lanes: the f = 0 partner sits in a different slot
+            const float4 *z2 = ex + ((((-l) & 3) + 4) & 31);
+#pragma unroll
+            for (int k0 = 0; k0 < 4; ++k0) {
+                if (l == 0 && k0 == 0) {
+                    b0[0] = d0[0];                              // k = 0: Z[M] == Z[0]
+                } else {
+                    float4 t = z2[32 * ((l == 0 ? 8 - k0 : 7 - k0) - 4)];
+                    b0[k0] = make_float2(t.x, t.y);
+                }
+            }
+        }
+        const uint64_t row = frame * p.pitch;
+#pragma unroll
+        for (int k0 = 0; k0 < 4; ++k0) {
+            float4 w = pwt[32 * k0];
+#pragma unroll
+            for (int f = 0; f < 2; ++f) {
+                const int k = kbase + 8 * f + 64 * k0;
+                const float2 a = f ? d1[k0] : d0[k0];
+                const float2 b = f ? b1[k0] : b0[k0];
+                const float2 tw = f ? make_float2(w.z, w.w) : make_float2(w.x, w.y);
+                float2 S = make_float2(a.x + b.x, a.y - b.y);
+                float2 D = make_float2(a.x - b.x, a.y + b.y);
+                float2 Q = cmul(D, tw);
+                emit<OUT, WIN>(p.out, row + k, S + Q);
+                emit<OUT, WIN>(p.out, row + (M - k), make_float2(S.x - Q.x, Q.y - S.y));
+            }
+        }
+        if (l == 0) emit<OUT, WIN>(p.out, row + M / 2, make_float2(2.0f * d0[4].x, -2.0f * d0[4].y));
+        __syncwarp();
+    }
+}
+
+}  // namespace kopek

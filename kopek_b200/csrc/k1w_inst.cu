@@ -1,0 +1,87 @@
+// Instantiations + host launcher of the warp-per-frame 1024-point kernel (fft_warp1024.cuh).
+#include <math.h>
+
+#include <vector>
+
+#include "k1w_launch.cuh"
+
+namespace kopek {
+
+// Host-side tables, built in f64 and rounded once to f32 (layout: see fft_warp1024.cuh).
+void k1w_build_tables(const float *half_window /* 1024 or nullptr */, float4 *out) {
+    const double tau = 2.0 * M_PI;
+    for (int i = 0; i < K1W_WIN_F4; ++i)
+        out[i] = half_window ? make_float4(half_window[4 * i], half_window[4 * i + 1], half_window[4 * i + 2],
+                                           half_window[4 * i + 3])
+                             : make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+    float4 *tpp = out + K1W_WIN_F4;
+    for (int k2 = 1; k2 < 8; ++k2)
+        for (int l = 0; l < 32; ++l) {
+            double a = -tau * (double)(l * k2) / 256.0, b = -tau * (double)((2 * l + 1) * k2) / 512.0;
+            tpp[(k2 - 1) * 32 + l] = make_float4((float)cos(a), (float)sin(a), (float)cos(b), (float)sin(b));
+        }
+    float4 *tq = tpp + K1W_TPP_F4;
+    for (int k1 = 1; k1 < 8; ++k1)
+        for (int b = 0; b < 4; ++b) {
+            double a = -tau * (double)(b * k1) / 32.0, c = -tau * (double)((2 * b + 1) * k1) / 64.0;
+            tq[(k1 - 1) * 4 + b] = make_float4((float)cos(a), (float)sin(a), (float)cos(c), (float)sin(c));
+        }
+    float4 *pw = tq + K1W_TQ_F4;
+    for (int k0 = 0; k0 < 4; ++k0)
+        for (int l = 0; l < 32; ++l) {
+            int k = (l >> 2) + 16 * (l & 3) + 64 * k0;
+            double a = tau * (double)k / 1024.0, b = tau * (double)(k + 8) / 1024.0;
+            pw[k0 * 32 + l] = make_float4((float)-sin(a), (float)-cos(a), (float)-sin(b), (float)-cos(b));
+        }
+}
+
+template <int OUT, bool WIN, int WARPS, int MINB>
+static cudaError_t launch_v(const K1WParams &p, int grid, cudaStream_t stream, int *occ_out) {
+    using G = K1WGeom<WARPS>;
+    auto kern = k1w_1024_kernel<OUT, WIN, WARPS, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+    if (e != cudaSuccess) return e;
+    if (occ_out) {
+        int nb = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, G::BLOCK, G::SMEM);
+        *occ_out = nb * WARPS;     // resident warps (= frames in flight) per SM
+        return e;
+    }
+    kern<<<grid, G::BLOCK, G::SMEM, stream>>>(p);
+    return cudaGetLastError();
+}
+
+template <int OUT, bool WIN>
+static cudaError_t launch_o(const K1WParams &p, int variant, int grid, cudaStream_t stream, int *occ_out) {
+    switch (variant) {
+        case 1: return launch_v<OUT, WIN, 8, 3>(p, grid, stream, occ_out);
+        case 2: return launch_v<OUT, WIN, 4, 4>(p, grid, stream, occ_out);
+        case 3: return launch_v<OUT, WIN, 4, 6>(p, grid, stream, occ_out);
+        case 4: return launch_v<OUT, WIN, 16, 1>(p, grid, stream, occ_out);
+        default: return launch_v<OUT, WIN, 8, 2>(p, grid, stream, occ_out);
+    }
+}
+
+int k1w_variant_warps(int variant) {
+    switch (variant) {
+        case 2: case 3: return 4;
+        case 4: return 16;
+        default: return 8;
+    }
+}
+
+cudaError_t k1w_launch(const K1WParams &p, int output, bool win, int variant, int grid, cudaStream_t stream,
+                       int *occ_out) {
+    switch (output * 2 + (win ? 1 : 0)) {
+        case 0: return launch_o<OUT_COMPLEX, false>(p, variant, grid, stream, occ_out);
+        case 1: return launch_o<OUT_COMPLEX, true>(p, variant, grid, stream, occ_out);
+        case 2: return launch_o<OUT_MAG, false>(p, variant, grid, stream, occ_out);
+        case 3: return launch_o<OUT_MAG, true>(p, variant, grid, stream, occ_out);
+        case 4: return launch_o<OUT_POWER, false>(p, variant, grid, stream, occ_out);
+        case 5: return launch_o<OUT_POWER, true>(p, variant, grid, stream, occ_out);
+        case 6: return launch_o<OUT_DB, false>(p, variant, grid, stream, occ_out);
+        default: return launch_o<OUT_DB, true>(p, variant, grid, stream, occ_out);
+    }
+}
+
+}  // namespace kopek

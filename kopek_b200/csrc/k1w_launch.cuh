@@ -1,0 +1,13 @@
+// Host-visible launcher of the warp-per-frame 1024-point kernel (k1w_inst.cu).
+#pragma once
+#include "fft_warp1024.cuh"
+
+namespace kopek {
+
+void k1w_build_tables(const float *half_window, float4 *out /* K1W_TABLE_F4 */);
+int k1w_variant_warps(int variant);
+// occ_out != nullptr: no launch, returns resident warps per SM for this variant.
+cudaError_t k1w_launch(const K1WParams &p, int output, bool win, int variant, int grid, cudaStream_t stream,
+                       int *occ_out);
+
+}  // namespace kopek

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "fft_c2c_f64.cuh"
 #include "k1_launch.cuh"
+#include "k1w_launch.cuh"
 
 namespace kopek {
 
@@ -229,6 +230,8 @@ struct kopek_plan {
     k1_launch_fn launch;
     float *d_win;      // 0.5 * w
     float2 *d_tw, *d_pw;
+    float4 *d_k1w;     // tables of the warp-per-frame kernel (n == 1024 only)
+    int k1w_variant, k1w_warps_per_sm;
     mutable uint32_t last_launches;
     // exec_host resources (lazy)
     std::mutex mu;
@@ -253,6 +256,11 @@ static kopek_status upload_window(kopek_plan *p, const float *w) {
     for (uint32_t i = 0; i < p->n; ++i) half[i] = 0.5f * w[i];
     if (!p->d_win) KOPEK_CUDA(cudaMalloc(&p->d_win, p->n * sizeof(float)));
     KOPEK_CUDA(cudaMemcpy(p->d_win, half.data(), p->n * sizeof(float), cudaMemcpyHostToDevice));
+    if (p->d_k1w) {
+        std::vector<float4> t(K1W_TABLE_F4);
+        k1w_build_tables(half.data(), t.data());
+        KOPEK_CUDA(cudaMemcpy(p->d_k1w, t.data(), sizeof(float4) * K1W_TABLE_F4, cudaMemcpyHostToDevice));
+    }
     return KOPEK_OK;
 }
 
@@ -260,6 +268,7 @@ static void plan_free_device(kopek_plan *p) {
     if (p->d_win) cudaFree(p->d_win);
     if (p->d_tw) cudaFree(p->d_tw);
     if (p->d_pw) cudaFree(p->d_pw);
+    if (p->d_k1w) cudaFree(p->d_k1w);
     for (HostSlot &s : p->slots) {
         if (s.d_in) cudaFree(s.d_in);
         if (s.d_out) cudaFree(s.d_out);
@@ -382,6 +391,7 @@ kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint
     p->bins = nb; p->pitch = out_pitch_elems; p->elem_bytes = output == KOPEK_OUT_COMPLEX ? 8 : 4;
     p->device = device; p->launch = launch; p->info = info();
     p->d_win = nullptr; p->d_tw = nullptr; p->d_pw = nullptr; p->last_launches = 0; p->slot_frames = 0;
+    p->d_k1w = nullptr; p->k1w_variant = 0; p->k1w_warps_per_sm = 0;
 
     kopek_status st = KOPEK_OK;
     do {
@@ -414,6 +424,28 @@ kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint
             (e = cudaMemcpy(p->d_pw, pw.data(), (M / 2 + 1) * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess) {
             st = fail(KOPEK_ERR_CUDA, "plan table upload failed: %s", cudaGetErrorString(e));
             break;
+        }
+        if (n == 1024) {
+            // headline size: warp-per-frame kernel (fft_warp1024.cuh); K1 stays for FULL bins / odd hops
+            const char *env = getenv("KOPEK_K1W_VARIANT");
+            p->k1w_variant = env ? atoi(env) : 0;
+            if (p->k1w_variant >= 0) {
+                std::vector<float4> t(K1W_TABLE_F4);
+                k1w_build_tables(nullptr, t.data());
+                if ((e = cudaMalloc(&p->d_k1w, sizeof(float4) * K1W_TABLE_F4)) != cudaSuccess ||
+                    (e = cudaMemcpy(p->d_k1w, t.data(), sizeof(float4) * K1W_TABLE_F4, cudaMemcpyHostToDevice)) !=
+                        cudaSuccess) {
+                    st = fail(KOPEK_ERR_CUDA, "K1W table upload failed: %s", cudaGetErrorString(e));
+                    break;
+                }
+                K1WParams dummy{};
+                e = k1w_launch(dummy, (int)output, window != KOPEK_WINDOW_RECT, p->k1w_variant, 0, nullptr,
+                               &p->k1w_warps_per_sm);
+                if (e != cudaSuccess || p->k1w_warps_per_sm <= 0) {
+                    st = fail(KOPEK_ERR_CUDA, "K1W kernel cannot be resident: %s", cudaGetErrorString(e));
+                    break;
+                }
+            }
         }
         if (window == KOPEK_WINDOW_HANN || window == KOPEK_WINDOW_HAMMING) {
             std::vector<float> w;
@@ -463,6 +495,22 @@ uint32_t kopek_plan_last_launches(const kopek_plan *plan) { return plan ? plan->
 
 static kopek_status stft_launch(const kopek_plan *plan, const float *d_samples, uint64_t frames, void *d_out,
                                 cudaStream_t stream) {
+    if (plan->d_k1w && plan->bins_mode == KOPEK_BINS_HALF && plan->hop % 4 == 0 && (uintptr_t)d_samples % 16 == 0) {
+        K1WParams wp;
+        wp.x = d_samples;
+        wp.out = d_out;
+        wp.tables = plan->d_k1w;
+        wp.n_frames = frames;
+        wp.hop = plan->hop;
+        wp.pitch = plan->pitch;
+        const uint64_t warps = (uint64_t)plan->sm_count * plan->k1w_warps_per_sm;
+        const int wpb = k1w_variant_warps(plan->k1w_variant);
+        const int grid = (int)std::min<uint64_t>((frames + wpb - 1) / wpb, warps / wpb);
+        cudaError_t e = k1w_launch(wp, (int)plan->output, plan->window != KOPEK_WINDOW_RECT, plan->k1w_variant, grid,
+                                   stream, nullptr);
+        if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "K1W launch failed: %s", cudaGetErrorString(e));
+        return KOPEK_OK;
+    }
     K1Params kp;
     kp.x = d_samples;
     kp.out = d_out;
