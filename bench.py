@@ -282,7 +282,7 @@ def run_ours(args):
                        "parallelism": f"frame-sharded x{world}, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": _ncu_traffic(), "peak_source": peak_src,
-                         "kernel": "k1_stft_kernel<1024,MAG,WIN>", "kernel_ms": kernel_ms,
+                         "kernel": "k1w_1024_kernel<MAG,WIN> (warp per frame, TMA prefetch)", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": frames * ALGO_BYTES_PER_FRAME},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                     "frames_per_step": ef, "steps": e2e_steps, "launches_per_step": e2e_launches,

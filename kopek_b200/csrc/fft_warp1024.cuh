@@ -41,10 +41,38 @@ constexpr int K1W_PW_F4 = 4 * 32;          // [k0][lane]    (-i W1024^{k}, -i W1
 constexpr int K1W_TABLE_F4 = K1W_WIN_F4 + K1W_TPP_F4 + K1W_TQ_F4 + K1W_PW_F4;
 constexpr int K1W_EX_F4 = 288;             // per-warp exchange buffer: 256 slots + 32 spare
 
-template <int WARPS> struct K1WGeom {
+constexpr int K1W_IN_F4 = 256;             // per-warp TMA landing buffer: one frame, linear
+
+template <int WARPS, bool TMA = false> struct K1WGeom {
     static constexpr int BLOCK = WARPS * 32;
-    static constexpr size_t SMEM = sizeof(float4) * (K1W_TABLE_F4 + WARPS * K1W_EX_F4);
+    static constexpr int WARP_F4 = K1W_EX_F4 + (TMA ? K1W_IN_F4 : 0);
+    // tables | per-warp (exchange [+ landing]) | per-warp mbarrier
+    static constexpr size_t SMEM = sizeof(float4) * (K1W_TABLE_F4 + WARPS * WARP_F4) + (TMA ? 8 * WARPS : 0);
 };
+
+// ---- TMA (bulk async copy) + mbarrier primitives: one frame = one 4096-byte cp.async.bulk ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "KOPEK_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra KOPEK_DONE;\n\t"
+        "bra KOPEK_WAIT;\n\t"
+        "KOPEK_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 
 __device__ __forceinline__ float4 ldg_stream(const float4 *p) {
     float4 r;
@@ -53,7 +81,35 @@ __device__ __forceinline__ float4 ldg_stream(const float4 *p) {
     return r;
 }
 
-template <int OUT, bool WIN, int WARPS, int MINB>
+// multiply by a compile-time constant (c, s): 2 FMUL + 2 FFMA with immediates
+__device__ __forceinline__ float2 cmul_const(float2 a, float c, float s) {
+    return make_float2(fmaf(-a.y, s, a.x * c), fmaf(a.y, c, a.x * s));
+}
+// W512^k and W64^k, k = 1..7 (the odd-element factors of passes A and B)
+__device__ __forceinline__ float2 mul_w512(float2 a, int k) {
+    constexpr float c[8] = {1.0f, 0.99992470183914454092f, 0.99969881869620422012f, 0.99932238458834950090f,
+                            0.99879545620517239271f, 0.99811811290014920526f, 0.99729045667869021614f,
+                            0.99631261218277801050f};
+    constexpr float s[8] = {0.0f, -0.01227153828571992608f, -0.02454122852291228803f, -0.03680722294135883231f,
+                            -0.04906767432741801426f, -0.06132073630220857779f, -0.07356456359966742631f,
+                            -0.08579731234443989385f};
+    return cmul_const(a, c[k], s[k]);
+}
+__device__ __forceinline__ float2 mul_w64(float2 a, int k) {
+    constexpr float c[8] = {1.0f, 0.99518472667219688624f, 0.98078528040323044913f, 0.95694033573220886494f,
+                            0.92387953251128675613f, 0.88192126434835502971f, 0.83146961230254523708f,
+                            0.77301045336273696081f};
+    constexpr float s[8] = {0.0f, -0.09801714032956060199f, -0.19509032201612826785f, -0.29028467725446236764f,
+                            -0.38268343236508977173f, -0.47139673682599764856f, -0.55557023301960222474f,
+                            -0.63439328416364549822f};
+    return cmul_const(a, c[k], s[k]);
+}
+
+// TWREG: pass-A/B twiddles live in registers (loop invariant per lane) instead of shared memory;
+// WINREG: so does the lane's slice of the window.
+// TMA: the NEXT frame of the warp is fetched by one cp.async.bulk into the warp's landing buffer while
+//      the current one is transformed (the buffer is free as soon as pass A has read it).
+template <int OUT, bool WIN, int WARPS, int MINB, bool TWREG, bool WINREG, bool TMA>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 k1w_1024_kernel(const K1WParams p) {
     constexpr int M = 512;
@@ -68,7 +124,10 @@ k1w_1024_kernel(const K1WParams p) {
     __syncthreads();
 
     const int l = threadIdx.x & 31;
-    float4 *ex = s_ex + (threadIdx.x >> 5) * K1W_EX_F4;
+    float4 *ex = s_ex + (threadIdx.x >> 5) * K1WGeom<WARPS, TMA>::WARP_F4;
+    const float4 *in = ex + K1W_EX_F4 + l;                   // TMA landing buffer, + 32 n2
+    uint64_t *bar = reinterpret_cast<uint64_t *>(s_ex + WARPS * K1WGeom<WARPS, TMA>::WARP_F4) + (threadIdx.x >> 5);
+    uint32_t phase = 0;
     float4 *exA = ex + l + (l >> 3);                         // + 36 k2
     float4 *exB = ex + 36 * (l >> 2) + (l & 3);              // + 4 n1 + (n1 >> 1)
     float4 *exC = ex + 36 * (l >> 2) + 9 * (l & 3);          // + 4 f + s
@@ -79,20 +138,60 @@ k1w_1024_kernel(const K1WParams p) {
     const float4 *pwt = s_pw + l;                            // + 32 k0
     const float4 *wt = s_win + l;                            // + 32 n2
     const int kbase = (l >> 2) + 16 * (l & 3);               // k = kbase + 8 f + 64 k0
+    float2 rp[8], rq[8];                                     // TWREG: W256^{l k2}, W32^{b k1}
+    float4 rw[8];                                            // WINREG: window slice
+    if constexpr (TWREG) {
+#pragma unroll
+        for (int k = 1; k < 8; ++k) {
+            float4 t = tpp[32 * (k - 1)], u = tq[4 * (k - 1)];
+            rp[k] = make_float2(t.x, t.y);
+            rq[k] = make_float2(u.x, u.y);
+        }
+    }
+    if constexpr (WIN && WINREG) {
+#pragma unroll
+        for (int n2 = 0; n2 < 8; ++n2) rw[n2] = wt[32 * n2];
+    }
 
     const uint64_t total_warps = (uint64_t)gridDim.x * WARPS;
-    for (uint64_t frame = (uint64_t)blockIdx.x * WARPS + (threadIdx.x >> 5); frame < p.n_frames;
-         frame += total_warps) {
+    const uint64_t first = (uint64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if constexpr (TMA) {
+        if (l == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (first < p.n_frames) {
+                mbar_expect_tx(bar, 4096);
+                tma_load_1d(ex + K1W_EX_F4, p.x + first * p.hop, 4096, bar);
+            }
+        }
+        __syncwarp();
+    }
+    for (uint64_t frame = first; frame < p.n_frames; frame += total_warps) {
         // ---- A: load + window, transform over n2, twiddle, publish
-        const float4 *xf = reinterpret_cast<const float4 *>(p.x + frame * p.hop) + l;
         float4 v[8];
+        if constexpr (TMA) {
+            mbar_wait(bar, phase);
+            phase ^= 1;
 #pragma unroll
-        for (int n2 = 0; n2 < 8; ++n2) v[n2] = ldg_stream(xf + 32 * n2);
+            for (int n2 = 0; n2 < 8; ++n2) v[n2] = in[32 * n2];
+            __syncwarp();                                    // every lane has its samples: the buffer is free
+            if (l == 0 && frame + total_warps < p.n_frames) {
+                mbar_expect_tx(bar, 4096);
+                tma_load_1d(ex + K1W_EX_F4, p.x + (frame + total_warps) * p.hop, 4096, bar);
+            }
+        } else {
+            const float4 *xf = reinterpret_cast<const float4 *>(p.x + frame * p.hop) + l;
+#pragma unroll
+            for (int n2 = 0; n2 < 8; ++n2) v[n2] = ldg_stream(xf + 32 * n2);
+        }
         float2 d0[8], d1[8];
 #pragma unroll
         for (int n2 = 0; n2 < 8; ++n2) {
             if constexpr (WIN) {
-                float4 w = wt[32 * n2];
+                float4 w;
+                if constexpr (WINREG) w = rw[n2];
+                else w = wt[32 * n2];
                 d0[n2] = make_float2(v[n2].x * w.x, v[n2].y * w.y);
                 d1[n2] = make_float2(v[n2].z * w.z, v[n2].w * w.w);
             } else {
@@ -105,9 +204,15 @@ k1w_1024_kernel(const K1WParams p) {
         exA[0] = make_float4(d0[0].x, d0[0].y, d1[0].x, d1[0].y);
 #pragma unroll
         for (int k2 = 1; k2 < 8; ++k2) {
-            float4 t = tpp[32 * (k2 - 1)];
-            float2 a = cmul(d0[k2], make_float2(t.x, t.y));
-            float2 b = cmul(d1[k2], make_float2(t.z, t.w));
+            float2 a, b;
+            if constexpr (TWREG) {
+                a = cmul(d0[k2], rp[k2]);
+                b = cmul(mul_w512(d1[k2], k2), rp[k2]);
+            } else {
+                float4 t = tpp[32 * (k2 - 1)];
+                a = cmul(d0[k2], make_float2(t.x, t.y));
+                b = cmul(d1[k2], make_float2(t.z, t.w));
+            }
             exA[36 * k2] = make_float4(a.x, a.y, b.x, b.y);
         }
         __syncwarp();
@@ -123,9 +228,15 @@ k1w_1024_kernel(const K1WParams p) {
         exB[0] = make_float4(d0[0].x, d0[0].y, d1[0].x, d1[0].y);
 #pragma unroll
         for (int k1 = 1; k1 < 8; ++k1) {
-            float4 t = tq[4 * (k1 - 1)];
-            float2 a = cmul(d0[k1], make_float2(t.x, t.y));
-            float2 b = cmul(d1[k1], make_float2(t.z, t.w));
+            float2 a, b;
+            if constexpr (TWREG) {
+                a = cmul(d0[k1], rq[k1]);
+                b = cmul(mul_w64(d1[k1], k1), rq[k1]);
+            } else {
+                float4 t = tq[4 * (k1 - 1)];
+                a = cmul(d0[k1], make_float2(t.x, t.y));
+                b = cmul(d1[k1], make_float2(t.z, t.w));
+            }
             exB[4 * k1 + (k1 >> 1)] = make_float4(a.x, a.y, b.x, b.y);
         }
         __syncwarp();

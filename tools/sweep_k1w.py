@@ -9,12 +9,12 @@ import torch  # noqa: E402
 from kopek_b200 import StftPlan  # noqa: E402
 
 frames = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
-variants = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [-1, 0, 1, 2, 3, 4]
+variants = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [-1] + list(range(14))
 n = 1024
 x = torch.randn(frames * n, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
 ref = None
-for window, output in ((1, 1), (0, 1), (1, 3), (1, 0)):
+for window, output in ((1, 1), (0, 1)):
     for v in variants:
         os.environ["KOPEK_K1W_VARIANT"] = str(v)
         plan = StftPlan(n, n, window, output)
