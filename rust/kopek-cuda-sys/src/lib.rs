@@ -1,0 +1,64 @@
+//! Raw FFI to libkopek_cuda.so -- one declaration per entry point of include/kopek_cuda.h.
+//! NOTE: written against the header; this repository's build image has no rustc/cargo, so
+//! these sources are not compiled here.  tests/cpp/test_dropin.cpp exercises the identical
+//! call sequences through the same C ABI.
+#![allow(non_camel_case_types)]
+
+use std::os::raw::{c_char, c_int, c_void};
+
+pub type kopek_status = i32;
+pub const KOPEK_OK: kopek_status = 0;
+pub const KOPEK_ERR_INVALID: kopek_status = -1;
+pub const KOPEK_ERR_CUDA: kopek_status = -2;
+pub const KOPEK_ERR_NOMEM: kopek_status = -3;
+pub const KOPEK_ERR_UNSUPPORTED: kopek_status = -4;
+
+pub const KOPEK_WINDOW_RECT: u32 = 0;
+pub const KOPEK_WINDOW_HANN: u32 = 1;
+pub const KOPEK_WINDOW_HAMMING: u32 = 2;
+pub const KOPEK_WINDOW_CUSTOM: u32 = 3;
+pub const KOPEK_OUT_COMPLEX: u32 = 0;
+pub const KOPEK_OUT_MAG: u32 = 1;
+pub const KOPEK_OUT_POWER: u32 = 2;
+pub const KOPEK_OUT_DB: u32 = 3;
+pub const KOPEK_BINS_HALF: u32 = 0;
+pub const KOPEK_BINS_FULL: u32 = 1;
+
+#[repr(C)]
+pub struct kopek_plan {
+    _private: [u8; 0],
+}
+
+extern "C" {
+    pub fn kopek_last_error() -> *const c_char;
+    pub fn kopek_version() -> *const c_char;
+    pub fn kopek_device_count() -> i32;
+
+    pub fn kopek_next_pow2(n: usize) -> usize;
+    /// `in_`/`out`: interleaved (re, im) f64 == `*const Complex<f64>` (num-complex is #[repr(C)]).
+    pub fn kopek_fft_c2c_f64(in_: *const f64, n_in: usize, out: *mut f64, n_out: usize) -> kopek_status;
+    pub fn kopek_fft_c2c_f64_batched(in_: *const f64, n_in: usize, batch: usize, out: *mut f64) -> kopek_status;
+    pub fn kopek_fft_c2c_f64_device(d_in: *const f64, n_in: usize, batch: usize, d_out: *mut f64, device: c_int,
+                                    cuda_stream: *mut c_void) -> kopek_status;
+    pub fn kopek_show_format(label: *const c_char, buf: *const f64, n: usize, dst: *mut c_char, cap: usize) -> usize;
+    pub fn kopek_show(label: *const c_char, buf: *const f64, n: usize) -> kopek_status;
+
+    pub fn kopek_plan_create(plan: *mut *mut kopek_plan, n: u32, hop: u32, window: u32, output: u32, bins: u32,
+                             out_pitch_elems: u64, device: c_int) -> kopek_status;
+    pub fn kopek_plan_set_window(plan: *mut kopek_plan, window_host: *const f32) -> kopek_status;
+    pub fn kopek_plan_destroy(plan: *mut kopek_plan) -> kopek_status;
+    pub fn kopek_plan_frames(plan: *const kopek_plan, n_samples: u64) -> u64;
+    pub fn kopek_plan_bins(plan: *const kopek_plan) -> u64;
+    pub fn kopek_plan_out_pitch(plan: *const kopek_plan) -> u64;
+    pub fn kopek_plan_out_elem_bytes(plan: *const kopek_plan) -> u64;
+    pub fn kopek_plan_last_launches(plan: *const kopek_plan) -> u32;
+    pub fn kopek_stft_exec(plan: *const kopek_plan, d_samples: *const f32, n_samples: u64, d_out: *mut c_void,
+                           n_frames_out: *mut u64, cuda_stream: *mut c_void) -> kopek_status;
+    pub fn kopek_stft_exec_host(plan: *mut kopek_plan, h_samples: *const f32, n_samples: u64, h_out: *mut c_void,
+                                n_frames_out: *mut u64) -> kopek_status;
+    pub fn kopek_host_alloc(ptr: *mut *mut c_void, bytes: usize) -> kopek_status;
+    pub fn kopek_host_free(ptr: *mut c_void) -> kopek_status;
+
+    pub fn kopek_fft_large_c2c_f32(d_in: *const f32, d_out: *mut f32, n: u64, device: c_int,
+                                   cuda_stream: *mut c_void) -> kopek_status;
+}

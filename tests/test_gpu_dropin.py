@@ -84,3 +84,20 @@ def test_show_prints_reference_format(built_lib, capfd):
     fft.show("label", [1 + 2j, -0.5 - 0.25j, 0j, complex(-0.0, -3.14159)])
     out = capfd.readouterr().out
     assert out == open(os.path.join(GOLDEN, "show.txt")).read()
+
+
+def test_cpp_mirror_harness(built_lib, oracle_mod, tmp_path):
+    """kopek::fft::fft / kopek::fft::show C++ mirror (kopek_b200/host/kopek_fft.hpp): the call sequences of the
+    Rust shim through the same C ABI, bit-compared with the oracle inside the harness."""
+    import subprocess
+    from conftest import ROOT
+    exe = str(tmp_path / "test_dropin")
+    libdir = os.path.dirname(built_lib)
+    odir = os.path.join(ROOT, "oracle", "_build")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_dropin.cpp"),
+                    "-L", libdir, "-lkopek_cuda", "-L", odir, "-lkopek_oracle",
+                    f"-Wl,-rpath,{libdir}", f"-Wl,-rpath,{odir}"], check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "DROPIN_OK" in r.stdout and "peak bin 10" in r.stdout
+    assert "spectrum\n" in r.stdout          # show() printed the label line
