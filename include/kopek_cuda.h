@@ -114,7 +114,9 @@ KOPEK_API kopek_status kopek_host_alloc(void **ptr, size_t bytes);   /* page-loc
 KOPEK_API kopek_status kopek_host_free(void *ptr);
 
 /* ---- 3. large single transform (four-step), device-resident c2c f32 ----------
- * n a power of two, 2^13 <= n <= 2^27; natural-order output; d_in != d_out. */
+ * Interleaved (re,im) f32, n a power of two with 2^16 <= n <= 2^24, natural-order unnormalised
+ * output, d_in != d_out, both 16-byte aligned.  Two HBM passes with TMA-staged tiles; asynchronous
+ * on cuda_stream.  Replaces one fft() call (src/fft.rs:6) on a long buffer. */
 KOPEK_API kopek_status kopek_fft_large_c2c_f32(const float *d_in, float *d_out, uint64_t n, int device,
                                                void *cuda_stream);
 

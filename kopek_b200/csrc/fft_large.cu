@@ -1,0 +1,328 @@
+// K3 -- large single complex FFT (n = N1 x N2 up to 2^24) as a four-step decomposition with
+// TMA-staged tiles (sm_100a).  BASELINE.json configs[3]: "single large 2^24-point FFT".
+//
+// The reference computes any length with one recursive call (src/fft.rs:6-41); for a 2^24-point
+// transform its two 256 MiB ping-pong buffers are walked with strides up to 2^23 elements.  Here:
+//
+//   n = n1 N2 + n2,  k = k1 + N1 k2
+//   pass 1 (one CTA per tile of 4 columns n2):  A[k1][n2] = W_n^{n2 k1} * sum_n1 x[n1 N2 + n2] W_N1^{n1 k1}
+//   pass 2 (one CTA per tile of 4 rows k1):     X[k1 + N1 k2] = sum_n2 A[k1][n2] W_N2^{n2 k2}
+//
+// Two HBM passes (the minimum for a transform that does not fit on chip).  Every global access is a
+// TMA tile: pass 1 loads a [N1 x 4] column tile with 2-D boxes (32-byte rows) and stores its result
+// TILE-MAJOR -- mid[k1/4][n2][k1%4], 128-byte segments -- so that pass 2 loads ONE contiguous block per
+// CTA (1-D bulk copies) and stores [N2 x 4] tiles of the natural-order output.  Both transposes and the
+// inter-step twiddle are fused into the passes; there is no standalone transpose kernel.
+// The sub-transforms are Stockham radix-4/8/16 in shared memory with the four tile columns interleaved
+// (column index fastest across lanes), which keeps every shared access contiguous.
+#include <cuda.h>
+#include <math.h>
+
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "fft_batched.cuh"
+#include "fft_warp1024.cuh"
+
+namespace kopek {
+
+template <int M> struct K3Cfg;
+template <> struct K3Cfg<256>  { static constexpr int R0 = 16, R1 = 16, R2 = 1; };
+template <> struct K3Cfg<512>  { static constexpr int R0 = 8,  R1 = 8,  R2 = 8; };
+template <> struct K3Cfg<1024> { static constexpr int R0 = 4,  R1 = 16, R2 = 16; };
+template <> struct K3Cfg<2048> { static constexpr int R0 = 8,  R1 = 16, R2 = 16; };
+template <> struct K3Cfg<4096> { static constexpr int R0 = 16, R1 = 16, R2 = 16; };
+
+__host__ __device__ constexpr int k3_swz(int q) { return q ^ ((q >> 4) & 15); }
+
+// One Stockham stage on 4 interleaved columns: element (q, c) lives at buf[pos(q) * 4 + c].
+// READ_LINEAR / WRITE_LINEAR select the dense layout TMA produced / consumes; otherwise the swizzled one.
+// FIRST_MAP remaps the logical index of the very first read (pass 2: tile-major block order).
+template <int RAD, int NS, int M, int T, bool READ_LINEAR, bool WRITE_LINEAR, bool TILE_MAJOR_IN>
+__device__ __forceinline__ void k3_stage(float2 *buf, const float2 *tw, int tid, int c) {
+    constexpr int NB = 16 / RAD;
+    float2 d[16];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        int j = tid + T * i;
+        int kk = j & (NS - 1);
+#pragma unroll
+        for (int t = 0; t < RAD; ++t) {
+            int q = j + t * (M / RAD);
+            int pos;
+            if constexpr (TILE_MAJOR_IN) pos = ((q >> 2) << 4) + (c << 2) + (q & 3);   // [q/4][c][q%4]
+            else pos = (READ_LINEAR ? q : k3_swz(q)) * 4 + c;
+            float2 v = buf[pos];
+            if (NS > 1 && t > 0) v = cmul(v, tw[kk * t * (M / (NS * RAD))]);
+            d[i * RAD + t] = v;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) Dft<RAD>::run(d + i * RAD);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        int j = tid + T * i;
+        int kk = j & (NS - 1);
+        int base = (j - kk) * RAD + kk;
+#pragma unroll
+        for (int k = 0; k < RAD; ++k) {
+            int q = base + k * NS;
+            buf[(WRITE_LINEAR ? q : k3_swz(q)) * 4 + c] = d[i * RAD + k];
+        }
+    }
+    __syncthreads();
+}
+
+// M-point FFT of the 4 interleaved columns in `buf`; result dense: buf[k * 4 + c].
+template <int M, bool TILE_MAJOR_IN>
+__device__ __forceinline__ void k3_fft_tile(float2 *buf, const float2 *tw, int tid, int c) {
+    using C = K3Cfg<M>;
+    constexpr int T = M / 16;
+    if constexpr (C::R2 > 1) {
+        k3_stage<C::R0, 1, M, T, true, false, TILE_MAJOR_IN>(buf, tw, tid, c);
+        k3_stage<C::R1, C::R0, M, T, false, false, false>(buf, tw, tid, c);
+        k3_stage<C::R2, C::R0 * C::R1, M, T, false, true, false>(buf, tw, tid, c);
+    } else {
+        k3_stage<C::R0, 1, M, T, true, false, TILE_MAJOR_IN>(buf, tw, tid, c);
+        k3_stage<C::R1, C::R0, M, T, false, true, false>(buf, tw, tid, c);
+    }
+}
+
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int x, int y, const void *src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(map), "r"(x), "r"(y), "r"(smem_u32(src)) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+struct K3Tables {
+    const float2 *tw_sub1;   // W_N1^e, e < N1  (stage twiddles of pass 1)
+    const float2 *tw_sub2;   // W_N2^e, e < N2
+    const float2 *tw_hi;     // W_n^{4096 h}, h < n/4096 (two-level inter-step twiddle)
+    const float2 *tw_lo;     // W_n^{l},      l < 4096
+};
+
+// ---- pass 1: column tile s = blockIdx.x (columns 4s..4s+3), all n1
+template <int N1>
+__global__ void __launch_bounds__(N1 / 4, 1)
+k3_pass1(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap mid_map, K3Tables tb) {
+    extern __shared__ __align__(128) unsigned char k3_smem[];
+    float2 *buf = reinterpret_cast<float2 *>(k3_smem);                 // N1 x 4 complex, dense
+    uint64_t *bar = reinterpret_cast<uint64_t *>(k3_smem + (size_t)N1 * 32);
+    const int s = blockIdx.x;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, N1 * 32);
+        for (int r0 = 0; r0 < N1; r0 += 256) tma_load_2d(buf + r0 * 4, &in_map, 8 * s, r0, bar);
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+    const int c = threadIdx.x & 3, tid = threadIdx.x >> 2;
+    k3_fft_tile<N1, false>(buf, tb.tw_sub1, tid, c);
+    // inter-step twiddle W_n^{n2 k1}, n2 = 4s + c; m = n2 k1 < n <= 2^24: W^m = W^{4096 (m>>12)} W^{m & 4095}
+    const uint32_t n2 = 4u * s + c;
+#pragma unroll 4
+    for (int k1 = tid; k1 < N1; k1 += N1 / 16) {
+        uint32_t m = n2 * (uint32_t)k1;
+        float2 w = cmul(__ldg(tb.tw_hi + (m >> 12)), __ldg(tb.tw_lo + (m & 4095u)));
+        buf[k1 * 4 + c] = cmul(buf[k1 * 4 + c], w);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic writes -> TMA store reads
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // buf is [k1][c] dense = rows u = k1/4 of 16 complex (32 floats): the 128-byte segments of mid
+        for (int u0 = 0; u0 < N1 / 4; u0 += 256) tma_store_2d(&mid_map, 32 * s, u0, buf + u0 * 16);
+        tma_store_commit_wait();
+    }
+}
+
+// ---- pass 2: row tile u = blockIdx.x (rows k1 = 4u..4u+3), all n2; block mid[u] is contiguous
+template <int N2>
+__global__ void __launch_bounds__(N2 / 4, 1)
+k3_pass2(const float2 *__restrict__ mid, const __grid_constant__ CUtensorMap out_map, K3Tables tb) {
+    extern __shared__ __align__(128) unsigned char k3_smem[];
+    float2 *buf = reinterpret_cast<float2 *>(k3_smem);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(k3_smem + (size_t)N2 * 32);
+    const int u = blockIdx.x;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, N2 * 32);
+        const char *src = reinterpret_cast<const char *>(mid) + (size_t)u * N2 * 32;
+        constexpr int CH = N2 * 32 < 16384 ? N2 * 32 : 16384;
+        for (int off = 0; off < N2 * 32; off += CH) tma_load_1d(k3_smem + off, src + off, CH, bar);
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+    const int c = threadIdx.x & 3, tid = threadIdx.x >> 2;
+    k3_fft_tile<N2, true>(buf, tb.tw_sub2, tid, c);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // buf is [k2][c] dense; out is [k2][k1] with k1 = 4u + c: 32-byte rows
+        for (int r0 = 0; r0 < N2; r0 += 256) tma_store_2d(&out_map, 8 * u, r0, buf + r0 * 4);
+        tma_store_commit_wait();
+    }
+}
+
+// ------------------------------------------------------------------------- host ----
+typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                              const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static encode_fn get_encode() {
+    static encode_fn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<encode_fn>(p);
+    });
+    return fn;
+}
+
+// 2-D f32 tensor map: `rows` rows of `row_floats` floats, box = box_floats x 256 rows.
+static bool make_map(CUtensorMap *m, const void *base, uint64_t row_floats, uint64_t rows, uint32_t box_floats,
+                     uint32_t box_rows) {
+    encode_fn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {row_floats, rows};
+    cuuint64_t strides[1] = {row_floats * sizeof(float)};
+    cuuint32_t box[2] = {box_floats, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct K3Plan {
+    uint64_t n = 0;
+    int device = -1;
+    int n1 = 0, n2 = 0;
+    float2 *tw1 = nullptr, *tw2 = nullptr, *hi = nullptr, *lo = nullptr, *mid = nullptr;
+};
+static std::mutex g_k3_mu;
+static std::vector<K3Plan> g_k3_plans;
+
+static void fill_twiddles(std::vector<float2> &v, uint64_t count, uint64_t step, uint64_t n) {
+    v.resize(count);
+    for (uint64_t i = 0; i < count; ++i) {
+        double th = -2.0 * M_PI * (double)(i * step) / (double)n;
+        v[i] = make_float2((float)cos(th), (float)sin(th));
+    }
+}
+
+static kopek_status k3_get_plan(uint64_t n, int device, K3Plan *out) {
+    std::lock_guard<std::mutex> lk(g_k3_mu);
+    for (const K3Plan &p : g_k3_plans)
+        if (p.n == n && p.device == device) { *out = p; return KOPEK_OK; }
+    int lg = 0;
+    while (((uint64_t)1 << lg) < n) ++lg;
+    K3Plan p;
+    p.n = n; p.device = device;
+    p.n1 = 1 << (lg / 2);
+    p.n2 = (int)(n / p.n1);
+    std::vector<float2> t1, t2, hi, lo;
+    fill_twiddles(t1, p.n1, 1, p.n1);
+    fill_twiddles(t2, p.n2, 1, p.n2);
+    fill_twiddles(hi, n / 4096, 4096, n);
+    fill_twiddles(lo, 4096, 1, n);
+    auto up = [](float2 **d, const std::vector<float2> &h) {
+        return cudaMalloc(d, h.size() * sizeof(float2)) == cudaSuccess &&
+               cudaMemcpy(*d, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice) == cudaSuccess;
+    };
+    if (!up(&p.tw1, t1) || !up(&p.tw2, t2) || !up(&p.hi, hi) || !up(&p.lo, lo) ||
+        cudaMalloc(&p.mid, n * sizeof(float2)) != cudaSuccess) {
+        cudaFree(p.tw1); cudaFree(p.tw2); cudaFree(p.hi); cudaFree(p.lo); cudaFree(p.mid);
+        return fail(KOPEK_ERR_NOMEM, "four-step plan for n=%llu: %s", (unsigned long long)n,
+                    cudaGetErrorString(cudaGetLastError()));
+    }
+    if (g_k3_plans.size() >= 4) {       // keep the cache (and its n-sized workspaces) small
+        cudaDeviceSynchronize();
+        K3Plan &o = g_k3_plans.front();
+        cudaFree(o.tw1); cudaFree(o.tw2); cudaFree(o.hi); cudaFree(o.lo); cudaFree(o.mid);
+        g_k3_plans.erase(g_k3_plans.begin());
+    }
+    g_k3_plans.push_back(p);
+    *out = p;
+    return KOPEK_OK;
+}
+
+template <int N1> static cudaError_t launch_pass1(int grid, const CUtensorMap &a, const CUtensorMap &b, K3Tables tb,
+                                                  cudaStream_t st) {
+    const int smem = N1 * 32 + 16;
+    cudaError_t e = cudaFuncSetAttribute(k3_pass1<N1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    k3_pass1<N1><<<grid, N1 / 4, smem, st>>>(a, b, tb);
+    return cudaGetLastError();
+}
+template <int N2> static cudaError_t launch_pass2(int grid, const float2 *mid, const CUtensorMap &o, K3Tables tb,
+                                                  cudaStream_t st) {
+    const int smem = N2 * 32 + 16;
+    cudaError_t e = cudaFuncSetAttribute(k3_pass2<N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    k3_pass2<N2><<<grid, N2 / 4, smem, st>>>(mid, o, tb);
+    return cudaGetLastError();
+}
+
+}  // namespace kopek
+
+using namespace kopek;
+
+extern "C" kopek_status kopek_fft_large_c2c_f32(const float *d_in, float *d_out, uint64_t n, int device,
+                                                void *cuda_stream) {
+    if (!d_in || !d_out) return fail(KOPEK_ERR_INVALID, "NULL device pointer");
+    if (d_in == d_out) return fail(KOPEK_ERR_INVALID, "in-place transform is not supported");
+    if (n < (1u << 16) || n > (1u << 24) || (n & (n - 1)))
+        return fail(KOPEK_ERR_UNSUPPORTED, "four-step transform: n=%llu must be a power of two in [2^16, 2^24]",
+                    (unsigned long long)n);
+    if (((uintptr_t)d_in | (uintptr_t)d_out) % 16) return fail(KOPEK_ERR_INVALID, "buffers must be 16-byte aligned");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(KOPEK_ERR_CUDA, "cannot select device %d", device);
+    K3Plan p;
+    kopek_status st = k3_get_plan(n, device, &p);
+    if (st != KOPEK_OK) return st;
+    CUtensorMap in_map, mid_map, out_map;
+    // in:  [N1 rows][N2 complex]          box 4 complex x 256 rows
+    // mid: [N1/4 rows][N2*4 complex]      box 16 complex x 256 rows (tile-major, 128-byte segments)
+    // out: [N2 rows][N1 complex]          box 4 complex x 256 rows
+    const uint32_t r1 = p.n1 < 256 ? p.n1 : 256, rm = p.n1 / 4 < 256 ? p.n1 / 4 : 256, r2 = p.n2 < 256 ? p.n2 : 256;
+    if (!make_map(&in_map, d_in, 2ull * p.n2, p.n1, 8, r1) ||
+        !make_map(&mid_map, p.mid, 8ull * p.n2, p.n1 / 4, 32, rm) ||
+        !make_map(&out_map, d_out, 2ull * p.n1, p.n2, 8, r2))
+        return fail(KOPEK_ERR_CUDA, "cuTensorMapEncodeTiled failed (driver entry point missing or bad geometry)");
+    K3Tables tb{p.tw1, p.tw2, p.hi, p.lo};
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (p.n1) {
+        case 256: e = launch_pass1<256>(p.n2 / 4, in_map, mid_map, tb, stream); break;
+        case 512: e = launch_pass1<512>(p.n2 / 4, in_map, mid_map, tb, stream); break;
+        case 1024: e = launch_pass1<1024>(p.n2 / 4, in_map, mid_map, tb, stream); break;
+        case 2048: e = launch_pass1<2048>(p.n2 / 4, in_map, mid_map, tb, stream); break;
+        case 4096: e = launch_pass1<4096>(p.n2 / 4, in_map, mid_map, tb, stream); break;
+    }
+    if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "four-step pass 1 (N1=%d): %s", p.n1, cudaGetErrorString(e));
+    switch (p.n2) {
+        case 256: e = launch_pass2<256>(p.n1 / 4, p.mid, out_map, tb, stream); break;
+        case 512: e = launch_pass2<512>(p.n1 / 4, p.mid, out_map, tb, stream); break;
+        case 1024: e = launch_pass2<1024>(p.n1 / 4, p.mid, out_map, tb, stream); break;
+        case 2048: e = launch_pass2<2048>(p.n1 / 4, p.mid, out_map, tb, stream); break;
+        case 4096: e = launch_pass2<4096>(p.n1 / 4, p.mid, out_map, tb, stream); break;
+        default: e = cudaErrorInvalidValue;
+    }
+    if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "four-step pass 2 (N2=%d): %s", p.n2, cudaGetErrorString(e));
+    return KOPEK_OK;
+}

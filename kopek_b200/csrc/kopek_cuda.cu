@@ -614,8 +614,4 @@ kopek_status kopek_host_free(void *ptr) {
     return KOPEK_OK;
 }
 
-kopek_status kopek_fft_large_c2c_f32(const float *, float *, uint64_t, int, void *) {
-    return fail(KOPEK_ERR_UNSUPPORTED, "four-step large transform: not built yet");
-}
-
 }  // extern "C"

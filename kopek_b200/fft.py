@@ -21,7 +21,7 @@ from . import _lib
 from ._lib import (BINS_FULL, BINS_HALF, OUT_COMPLEX, OUT_DB, OUT_MAG, OUT_POWER, WINDOW_CUSTOM, WINDOW_HAMMING,
                    WINDOW_HANN, WINDOW_RECT, KopekError, check)
 
-__all__ = ["fft", "fft_batched", "show", "show_format", "StftPlan", "next_pow2", "KopekError",
+__all__ = ["fft", "fft_batched", "fft_large_device", "show", "show_format", "StftPlan", "next_pow2", "KopekError",
            "WINDOW_RECT", "WINDOW_HANN", "WINDOW_HAMMING", "WINDOW_CUSTOM",
            "OUT_COMPLEX", "OUT_MAG", "OUT_POWER", "OUT_DB", "BINS_HALF", "BINS_FULL"]
 
@@ -47,6 +47,12 @@ def fft_batched(frames) -> np.ndarray:
     check(_lib.load().kopek_fft_c2c_f64_batched(a.ctypes.data if a.size else None, a.shape[1], a.shape[0],
                                                 out.ctypes.data))
     return out
+
+
+def fft_large_device(d_in: int, d_out: int, n: int, device: int = 0, stream: int = 0) -> None:
+    """Four-step complex f32 FFT of one long device-resident buffer (kopek_fft_large_c2c_f32):
+    n interleaved (re,im) pairs at d_in -> n at d_out, natural order, asynchronous on `stream`."""
+    check(_lib.load().kopek_fft_large_c2c_f32(d_in, d_out, n, device, stream or None))
 
 
 def show_format(label: str, buf) -> str:
