@@ -27,12 +27,12 @@ __host__ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 }
 __device__ __forceinline__ float fast_sqrt(float v) {
     float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
     return r;
 }
 __device__ __forceinline__ float fast_log2(float v) {
     float r;
-    asm("lg2.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
     return r;
 }
 
@@ -123,20 +123,26 @@ struct K1Params {
     int vec;               // 1: 8-byte sample loads allowed (hop even, base 8-byte aligned)
 };
 
+// Epilogue of one bin.  `dst` points at the bin's element (float, or float2 for OUT_COMPLEX).
+// X is 2x the spectrum when no window was applied (the 0.5 lives in the window table).
 template <int OUT, bool WIN>
-__device__ __forceinline__ void emit(void *out, uint64_t idx, float2 X) {
-    // X is 2x the spectrum when no window was applied (the 0.5 lives in the window table)
+__device__ __forceinline__ void emit_at(void *dst, float2 X) {
     if constexpr (OUT == OUT_COMPLEX) {
         constexpr float sc = WIN ? 1.0f : 0.5f;
-        reinterpret_cast<float2 *>(out)[idx] = make_float2(X.x * sc, X.y * sc);
+        *reinterpret_cast<float2 *>(dst) = make_float2(X.x * sc, X.y * sc);
     } else {
         float p = X.x * X.x + X.y * X.y;
         float r;
         if constexpr (OUT == OUT_MAG) r = WIN ? fast_sqrt(p) : 0.5f * fast_sqrt(p);
         else if constexpr (OUT == OUT_POWER) r = WIN ? p : 0.25f * p;
         else r = fmaf(fast_log2(p), 3.01029995663981195f, WIN ? 0.0f : -6.02059991327962390f);
-        reinterpret_cast<float *>(out)[idx] = r;
+        *reinterpret_cast<float *>(dst) = r;
     }
+}
+template <int OUT, bool WIN>
+__device__ __forceinline__ void emit(void *out, uint64_t idx, float2 X) {
+    constexpr int EB = OUT == OUT_COMPLEX ? 8 : 4;
+    emit_at<OUT, WIN>(reinterpret_cast<char *>(out) + idx * EB, X);
 }
 
 template <int RAD, int NS, int M, int T, class G>

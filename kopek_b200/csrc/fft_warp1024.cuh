@@ -138,14 +138,16 @@ k1w_1024_kernel(const K1WParams p) {
     const float4 *pwt = s_pw + l;                            // + 32 k0
     const float4 *wt = s_win + l;                            // + 32 n2
     const int kbase = (l >> 2) + 16 * (l & 3);               // k = kbase + 8 f + 64 k0
-    float2 rp[8], rq[8];                                     // TWREG: W256^{l k2}, W32^{b k1}
+    float2 rp[8], rp1[8], rq[8], rq1[8];                     // TWREG: W256^{l k2}, W512^{(2l+1) k2}, W32^{b k1}, W64^{(2b+1) k1}
     float4 rw[8];                                            // WINREG: window slice
     if constexpr (TWREG) {
 #pragma unroll
         for (int k = 1; k < 8; ++k) {
             float4 t = tpp[32 * (k - 1)], u = tq[4 * (k - 1)];
             rp[k] = make_float2(t.x, t.y);
+            rp1[k] = make_float2(t.z, t.w);
             rq[k] = make_float2(u.x, u.y);
+            rq1[k] = make_float2(u.z, u.w);
         }
     }
     if constexpr (WIN && WINREG) {
@@ -207,7 +209,7 @@ k1w_1024_kernel(const K1WParams p) {
             float2 a, b;
             if constexpr (TWREG) {
                 a = cmul(d0[k2], rp[k2]);
-                b = cmul(mul_w512(d1[k2], k2), rp[k2]);
+                b = cmul(d1[k2], rp1[k2]);
             } else {
                 float4 t = tpp[32 * (k2 - 1)];
                 a = cmul(d0[k2], make_float2(t.x, t.y));
@@ -231,7 +233,7 @@ k1w_1024_kernel(const K1WParams p) {
             float2 a, b;
             if constexpr (TWREG) {
                 a = cmul(d0[k1], rq[k1]);
-                b = cmul(mul_w64(d1[k1], k1), rq[k1]);
+                b = cmul(d1[k1], rq1[k1]);
             } else {
                 float4 t = tq[4 * (k1 - 1)];
                 a = cmul(d0[k1], make_float2(t.x, t.y));
@@ -276,24 +278,27 @@ k1w_1024_kernel(const K1WParams p) {
                 }
             }
         }
-        const uint64_t row = frame * p.pitch;
+        // bins k = kbase + (8 f + 64 k0) ascend from o_lo, bins M - k descend from o_hi: immediates only
+        constexpr int EB = OUT == OUT_COMPLEX ? 8 : 4;
+        char *o_lo = reinterpret_cast<char *>(p.out) + (frame * p.pitch + kbase) * EB;
+        char *o_hi = reinterpret_cast<char *>(p.out) + (frame * p.pitch + (M - kbase)) * EB;
 #pragma unroll
         for (int k0 = 0; k0 < 4; ++k0) {
             float4 w = pwt[32 * k0];
 #pragma unroll
             for (int f = 0; f < 2; ++f) {
-                const int k = kbase + 8 * f + 64 * k0;
+                const int koff = (8 * f + 64 * k0) * EB;
                 const float2 a = f ? d1[k0] : d0[k0];
                 const float2 b = f ? b1[k0] : b0[k0];
                 const float2 tw = f ? make_float2(w.z, w.w) : make_float2(w.x, w.y);
                 float2 S = make_float2(a.x + b.x, a.y - b.y);
                 float2 D = make_float2(a.x - b.x, a.y + b.y);
                 float2 Q = cmul(D, tw);
-                emit<OUT, WIN>(p.out, row + k, S + Q);
-                emit<OUT, WIN>(p.out, row + (M - k), make_float2(S.x - Q.x, Q.y - S.y));
+                emit_at<OUT, WIN>(o_lo + koff, S + Q);
+                emit_at<OUT, WIN>(o_hi - koff, make_float2(S.x - Q.x, Q.y - S.y));
             }
         }
-        if (l == 0) emit<OUT, WIN>(p.out, row + M / 2, make_float2(2.0f * d0[4].x, -2.0f * d0[4].y));
+        if (l == 0) emit_at<OUT, WIN>(o_lo + (M / 2) * EB, make_float2(2.0f * d0[4].x, -2.0f * d0[4].y));
         __syncwarp();
     }
 }

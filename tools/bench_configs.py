@@ -1,0 +1,88 @@
+#!/usr/bin/env python3
+"""Time every BASELINE.json config (not only the headline) on one GPU and print a markdown table.
+
+  configs[0] single 1024-pt fft() drop-in call (latency, host buffers)         -> K2
+  configs[1] 60 s 48 kHz chirp, Hann 2048, hop 512, dB                         -> K1
+  configs[2] 1M x 256-pt white noise, |X|                                       -> K1
+  configs[3] single 2^24-point c2c f32                                          -> K3
+  configs[4] (per-GPU shard) 8ch x 8h x 48 kHz, Hann 4096, hop 1024, |X|       -> K1 (1/64 of the job here)
+  M          2^20 x 1024 Hann |X|                                               -> K1W
+Roofline denominator: MEASURED_PEAKS.json hbm_gbs.  Algorithmic bytes as in SURVEY.md 8d.
+"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from kopek_b200 import OUT_DB, OUT_MAG, WINDOW_HANN, WINDOW_RECT, StftPlan, fft, signals  # noqa: E402
+
+try:
+    PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    PEAK = 6650.0
+st = torch.cuda.current_stream().cuda_stream
+
+
+def timed(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+rows = []
+
+
+def stft_case(name, n, hop, window, output, n_samples, gen=None):
+    x = torch.randn(n_samples, device="cuda") if gen is None else torch.from_numpy(gen).cuda()
+    plan = StftPlan(n, hop, window, output)
+    frames = plan.frames(n_samples)
+    out = torch.empty((frames, plan.pitch), device="cuda")
+    ms = timed(lambda: plan.exec_ptr(x.data_ptr(), n_samples, out.data_ptr(), st))
+    by = n_samples * 4 + frames * plan.bins * 4
+    rows.append((name, f"{frames} frames", ms, by, frames * n / ms / 1e6))
+    plan.close()
+
+
+# M
+stft_case("M: 2^20 x 1024 Hann |X| (K1W)", 1024, 1024, WINDOW_HANN, OUT_MAG, (1 << 20) * 1024)
+# configs[1]
+stft_case("cfg1: 60 s chirp, Hann 2048 hop 512 dB (K1)", 2048, 512, WINDOW_HANN, OUT_DB, 2880000,
+          gen=signals.chirp(2880000, 48000.0, 20.0, 20000.0))
+# configs[2]
+stft_case("cfg2: 1M x 256 white noise |X| (K1)", 256, 256, WINDOW_RECT, OUT_MAG, 1000000 * 256)
+# configs[4], one GPU's shard of one channel-hour-ish: 2^27 samples
+stft_case("cfg4 shard: 2^27 samples, Hann 4096 hop 1024 |X| (K1)", 4096, 1024, WINDOW_HANN, OUT_MAG, 1 << 27)
+stft_case("512-pt: 2^21 x 512 Hann |X| (K1)", 512, 512, WINDOW_HANN, OUT_MAG, (1 << 21) * 512)
+stft_case("2048-pt: 2^19 x 2048 Hann |X| (K1)", 2048, 2048, WINDOW_HANN, OUT_MAG, (1 << 19) * 2048)
+stft_case("4096-pt: 2^18 x 4096 Hann |X| (K1)", 4096, 4096, WINDOW_HANN, OUT_MAG, (1 << 18) * 4096)
+stft_case("1024-pt STFT hop 256: 2^28 samples Hann |X| (K1W)", 1024, 256, WINDOW_HANN, OUT_MAG, 1 << 28)
+# configs[3]
+for lg in (20, 22, 24):
+    n = 1 << lg
+    a = torch.randn(n, dtype=torch.complex64, device="cuda")
+    b = torch.empty_like(a)
+    ms = timed(lambda: fft.fft_large_device(a.data_ptr(), b.data_ptr(), n, 0, st))
+    rows.append((f"cfg3: single 2^{lg} c2c f32 four-step (K3)", "1 transform", ms, 2 * n * 8, n / ms / 1e6))
+# configs[0]: host-to-host latency of one drop-in call
+x = (np.random.default_rng(0).standard_normal(1024)).astype(np.complex128)
+fft.fft(x)
+t0 = time.perf_counter()
+for _ in range(200):
+    fft.fft(x)
+lat = (time.perf_counter() - t0) / 200 * 1e6
+
+print(f"| config | units | ms | algorithmic GB/s | % of {PEAK:.1f} GB/s | G samples/s |\n|---|---|---:|---:|---:|---:|")
+for name, units, ms, by, gs in rows:
+    print(f"| {name} | {units} | {ms:.4f} | {by / ms / 1e6:.1f} | {100 * by / ms / 1e6 / PEAK:.1f} | {gs:.1f} |")
+print(f"\ncfg0: one 1024-pt fft() drop-in call, host buffers in/out (K2): {lat:.1f} us per call")
