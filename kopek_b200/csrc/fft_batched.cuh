@@ -14,6 +14,7 @@
 // Each frame is owned by T = M/16 threads holding 16 complex values each.
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 namespace kopek {
@@ -99,6 +100,25 @@ template <> struct K1Cfg<1024> { static constexpr int S = 3, R0 = 8,  R1 = 8,  R
 template <> struct K1Cfg<2048> { static constexpr int S = 3, R0 = 4,  R1 = 16, R2 = 16; static constexpr int SWZ_SHIFT = 4; };
 template <> struct K1Cfg<4096> { static constexpr int S = 3, R0 = 8,  R1 = 16, R2 = 16; static constexpr int SWZ_SHIFT = 4; };
 
+// Host: fill the M-entry stage-twiddle table of frame size N_ (stage 1 block, then stage 2 block).
+template <int N_> inline void k1_build_stage_twiddles(float2 *out) {
+    using C = K1Cfg<N_>;
+    constexpr int M = N_ / 2;
+    const double tau = 6.283185307179586476925286766559;
+    for (int i = 0; i < M; ++i) out[i] = make_float2(1.0f, 0.0f);
+    int off = 0;
+    const int rad[2] = {C::R1, C::R2}, ns[2] = {C::R0, C::R0 * C::R1};
+    for (int s = 0; s < 2; ++s) {
+        if (rad[s] <= 1) break;
+        for (int t = 1; t < rad[s]; ++t)
+            for (int kk = 0; kk < ns[s]; ++kk) {
+                double th = -tau * (double)(kk * t) / (double)(ns[s] * rad[s]);
+                out[off + (t - 1) * ns[s] + kk] = make_float2((float)cos(th), (float)sin(th));
+            }
+        off += (rad[s] - 1) * ns[s];
+    }
+}
+
 template <int N_> struct K1Geom {
     using C = K1Cfg<N_>;
     static constexpr int N = N_, M = N_ / 2, R = 16, T = M / R;
@@ -114,7 +134,7 @@ struct K1Params {
     const float *x;        // samples
     void *out;             // spectra
     const float *win;      // N window coefficients, pre-scaled by 0.5 (nullptr: rectangular)
-    const float2 *tw;      // W_M^e = exp(-2 pi i e / M), e < M
+    const float2 *tw;      // per-stage t-major twiddle tables, M entries (k1_build_stage_twiddles)
     const float2 *pw;      // -i W_N^k = (-sin, -cos)(2 pi k / N), k <= M/2
     uint64_t n_frames;
     uint64_t hop;
@@ -158,6 +178,8 @@ __device__ __forceinline__ void stage_write(float2 *buf, const float2 *d, int ti
     }
 }
 
+// tw is the stage's own table, t-major: tw[(t-1) * NS + kk] = W_M^{kk t M/(NS RAD)}, so that lanes with
+// consecutive kk read consecutive words (no bank conflicts; v1 indexed one W_M^e table with stride kk*t).
 template <int RAD, int NS, int M, int T, class G>
 __device__ __forceinline__ void stage_read_twiddle(const float2 *buf, const float2 *tw, float2 *d, int tid) {
     constexpr int NB = 16 / RAD;
@@ -168,7 +190,7 @@ __device__ __forceinline__ void stage_read_twiddle(const float2 *buf, const floa
 #pragma unroll
         for (int t = 0; t < RAD; ++t) {
             float2 v = buf[G::swz(j + t * (M / RAD))];
-            if (t > 0) v = cmul(v, tw[kk * t * (M / (NS * RAD))]);
+            if (t > 0) v = cmul(v, tw[(t - 1) * NS + kk]);
             d[i * RAD + t] = v;
         }
     }
@@ -243,7 +265,7 @@ k1_stft_kernel(const K1Params p) {
         frame_sync<T>();
         // ---- stage 2
         if constexpr (R2 > 1) {
-            stage_read_twiddle<R2, R0 * R1, M, T, G>(buf, s_tw, d, tid);
+            stage_read_twiddle<R2, R0 * R1, M, T, G>(buf, s_tw + (R1 - 1) * R0, d, tid);
             stage_dft<R2>(d);
             frame_sync<T>();
             stage_write<R2, R0 * R1, M, T, G>(buf, d, tid);

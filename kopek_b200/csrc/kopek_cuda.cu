@@ -409,9 +409,12 @@ kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint
                                            cudaGetErrorString(cudaGetLastError())); break; }
         const uint32_t M = n / 2;
         std::vector<float2> tw(M), pw(M / 2 + 1);
-        for (uint32_t e2 = 0; e2 < M; ++e2) {
-            double th = -2.0 * M_PI * (double)e2 / (double)M;
-            tw[e2] = make_float2((float)cos(th), (float)sin(th));
+        switch (n) {
+            case 256: k1_build_stage_twiddles<256>(tw.data()); break;
+            case 512: k1_build_stage_twiddles<512>(tw.data()); break;
+            case 1024: k1_build_stage_twiddles<1024>(tw.data()); break;
+            case 2048: k1_build_stage_twiddles<2048>(tw.data()); break;
+            default: k1_build_stage_twiddles<4096>(tw.data()); break;
         }
         for (uint32_t k = 0; k <= M / 2; ++k) {
             double th = 2.0 * M_PI * (double)k / (double)n;
