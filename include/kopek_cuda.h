@@ -48,7 +48,18 @@ enum { KOPEK_WINDOW_RECT = 0, KOPEK_WINDOW_HANN = 1, KOPEK_WINDOW_HAMMING = 2, K
  * one output element = 8 bytes; all others: one f32 per bin.
  * MAG = |X| (norm(), beep/view.rs:155; equals the f32 sqrt-of-squares of
  * graph/utils.rs:53 up to rounding); POWER = |X|^2; DB = 20*log10|X|. */
-enum { KOPEK_OUT_COMPLEX = 0, KOPEK_OUT_MAG = 1, KOPEK_OUT_POWER = 2, KOPEK_OUT_DB = 3 };
+enum {
+    KOPEK_OUT_COMPLEX = 0, KOPEK_OUT_MAG = 1, KOPEK_OUT_POWER = 2, KOPEK_OUT_DB = 3,
+    /* Fused band epilogues (n = 1024, HALF bins only): no spectrum is written; each frame yields
+     * KOPEK_BAND_ROW = 10 f32: eight band means of scale*|X| followed by the peak pick of
+     * examples/pong/main.rs:200-207 -- index of the strictly largest mean (as f32; 0 if none > 0)
+     * and that mean.  BANDS_LOG: consecutive bands of 4,4,8,16,32,64,128,256 bins from bin 0
+     * (examples/graph/utils.rs:85-116, examples/pong/utils.rs:62-94); BANDS_LOW: eight bands of
+     * 3 bins from bin 20 (examples/pong/utils.rs:96-114).  scale: kopek_plan_set_band_scale
+     * (10 000 in graph/utils.rs:56, 100 in pong/utils.rs:41; default 1). */
+    KOPEK_OUT_BANDS_LOG = 4, KOPEK_OUT_BANDS_LOW = 5
+};
+#define KOPEK_BAND_ROW 10
 /* HALF: bins 0..n/2 (n/2+1 per frame, real input makes the rest redundant);
  * FULL: all n bins, as the reference's callers see them (graph/utils.rs:50 iterates all). */
 enum { KOPEK_BINS_HALF = 0, KOPEK_BINS_FULL = 1 };
@@ -90,6 +101,8 @@ KOPEK_API kopek_status kopek_show(const char *label, const double *buf, size_t n
 typedef struct kopek_plan kopek_plan;
 KOPEK_API kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint32_t window,
                                          uint32_t output, uint32_t bins, uint64_t out_pitch_elems, int device);
+/* Display scale of the band epilogues (KOPEK_OUT_BANDS_*); takes effect at the next execute. */
+KOPEK_API kopek_status kopek_plan_set_band_scale(kopek_plan *plan, float scale);
 /* Replace the window by n caller-supplied f32 coefficients (host pointer). */
 KOPEK_API kopek_status kopek_plan_set_window(kopek_plan *plan, const float *window_host);
 KOPEK_API kopek_status kopek_plan_destroy(kopek_plan *plan);

@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libkopek_cuda.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 WINDOW_RECT, WINDOW_HANN, WINDOW_HAMMING, WINDOW_CUSTOM = 0, 1, 2, 3
-OUT_COMPLEX, OUT_MAG, OUT_POWER, OUT_DB = 0, 1, 2, 3
+OUT_COMPLEX, OUT_MAG, OUT_POWER, OUT_DB, OUT_BANDS_LOG, OUT_BANDS_LOW = 0, 1, 2, 3, 4, 5
+BAND_ROW = 10
 BINS_HALF, BINS_FULL = 0, 1
 
 # every symbol include/kopek_cuda.h declares: name -> (restype, argtypes)
@@ -31,6 +32,7 @@ SYMBOLS = {
     "kopek_show": (_i32, [C.c_char_p, _vp, _sz]),
     "kopek_plan_create": (_i32, [C.POINTER(_vp), _u32, _u32, _u32, _u32, _u32, _u64, C.c_int]),
     "kopek_plan_set_window": (_i32, [_vp, _vp]),
+    "kopek_plan_set_band_scale": (_i32, [_vp, C.c_float]),
     "kopek_plan_destroy": (_i32, [_vp]),
     "kopek_plan_frames": (_u64, [_vp, _u64]),
     "kopek_plan_bins": (_u64, [_vp]),

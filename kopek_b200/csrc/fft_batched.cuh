@@ -19,7 +19,7 @@
 
 namespace kopek {
 
-enum : int { OUT_COMPLEX = 0, OUT_MAG = 1, OUT_POWER = 2, OUT_DB = 3 };
+enum : int { OUT_COMPLEX = 0, OUT_MAG = 1, OUT_POWER = 2, OUT_DB = 3, OUT_BANDS_LOG = 4, OUT_BANDS_LOW = 5 };
 
 __host__ __device__ __forceinline__ float2 operator+(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __host__ __device__ __forceinline__ float2 operator-(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }

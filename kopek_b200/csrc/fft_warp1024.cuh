@@ -32,6 +32,7 @@ struct K1WParams {
     uint64_t n_frames;
     uint64_t hop;
     uint64_t pitch;
+    float band_scale;        // OUT_BANDS_*: display scale applied to the band means
 };
 
 constexpr int K1W_WIN_F4 = 256;            // 0.5 * w[4i .. 4i+3]
@@ -103,6 +104,19 @@ __device__ __forceinline__ float2 mul_w64(float2 a, int k) {
                             -0.38268343236508977173f, -0.47139673682599764856f, -0.55557023301960222474f,
                             -0.63439328416364549822f};
     return cmul_const(a, c[k], s[k]);
+}
+
+// ---- fused band epilogue (OUT_BANDS_LOG / OUT_BANDS_LOW) -----------------------------------------
+// acc[b] += y for the band b that bin k falls in; only bands LO..HI are possible for this call site.
+template <int LO, int HI> __device__ __forceinline__ void band_add(float (&acc)[8], int band, float y) {
+#pragma unroll
+    for (int b = LO; b <= HI; ++b) acc[b] += band == b ? y : 0.0f;
+}
+// log-spaced bands [0,4) [4,8) [8,16) ... [256,512): index = max(0, floor(log2 k) - 1)
+__device__ __forceinline__ int band_log_of(int k) { return max(0, 30 - __clz(k)); }
+// eight 3-bin bands from bin 20: index (k - 20) / 3 for 20 <= k < 44, else none (-1)
+__device__ __forceinline__ int band_low_of(int k) {
+    return (k >= 20 && k < 44) ? ((k - 20) * 11) >> 5 : -1;      // x*11>>5 == x/3 for 0 <= x < 24
 }
 
 // TWREG: pass-A/B twiddles live in registers (loop invariant per lane) instead of shared memory;
@@ -279,6 +293,8 @@ k1w_1024_kernel(const K1WParams p) {
             }
         }
         // bins k = kbase + (8 f + 64 k0) ascend from o_lo, bins M - k descend from o_hi: immediates only
+        constexpr bool BANDS = OUT == OUT_BANDS_LOG || OUT == OUT_BANDS_LOW;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         constexpr int EB = OUT == OUT_COMPLEX ? 8 : 4;
         char *o_lo = reinterpret_cast<char *>(p.out) + (frame * p.pitch + kbase) * EB;
         char *o_hi = reinterpret_cast<char *>(p.out) + (frame * p.pitch + (M - kbase)) * EB;
@@ -294,11 +310,57 @@ k1w_1024_kernel(const K1WParams p) {
                 float2 S = make_float2(a.x + b.x, a.y - b.y);
                 float2 D = make_float2(a.x - b.x, a.y + b.y);
                 float2 Q = cmul(D, tw);
-                emit_at<OUT, WIN>(o_lo + koff, S + Q);
-                emit_at<OUT, WIN>(o_hi - koff, make_float2(S.x - Q.x, Q.y - S.y));
+                if constexpr (BANDS) {
+                    // |X[k]| joins its band; |X[M-k]| (bins 256..511) is band 7 of the log set
+                    const float2 X1 = S + Q;
+                    const float y1 = (WIN ? 1.0f : 0.5f) * fast_sqrt(X1.x * X1.x + X1.y * X1.y);
+                    const int k = kbase + 8 * f + 64 * k0;
+                    if constexpr (OUT == OUT_BANDS_LOG) {
+                        if (k0 == 0 && f == 0) band_add<0, 4>(acc, band_log_of(k), y1);
+                        else if (k0 == 0) band_add<2, 5>(acc, band_log_of(k), y1);
+                        else if (k0 == 1 && f == 0) acc[5] += y1;
+                        else if (k0 == 1) band_add<5, 6>(acc, band_log_of(k), y1);
+                        else if (k0 == 2 || f == 0) acc[6] += y1;
+                        else band_add<6, 7>(acc, band_log_of(k), y1);
+                        const float2 X2 = make_float2(S.x - Q.x, Q.y - S.y);
+                        const float y2 = (WIN ? 1.0f : 0.5f) * fast_sqrt(X2.x * X2.x + X2.y * X2.y);
+                        if (k0 == 0 && f == 0) acc[7] += k > 0 ? y2 : 0.0f;      // k = 0 pairs with bin 512: not in a band
+                        else acc[7] += y2;
+                    } else {
+                        if (k0 == 0) band_add<0, 7>(acc, band_low_of(k), y1);
+                    }
+                } else {
+                    emit_at<OUT, WIN>(o_lo + koff, S + Q);
+                    emit_at<OUT, WIN>(o_hi - koff, make_float2(S.x - Q.x, Q.y - S.y));
+                }
             }
         }
-        if (l == 0) emit_at<OUT, WIN>(o_lo + (M / 2) * EB, make_float2(2.0f * d0[4].x, -2.0f * d0[4].y));
+        if constexpr (BANDS) {
+            if constexpr (OUT == OUT_BANDS_LOG) {   // bin 256 = conj Z[256] (lane 0) is in band 7
+                if (l == 0) acc[7] += (WIN ? 2.0f : 1.0f) * fast_sqrt(d0[4].x * d0[4].x + d0[4].y * d0[4].y);
+            }
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], sft);
+            }
+            if (l == 0) {
+                constexpr float inv_log[8] = {1.f / 4, 1.f / 4, 1.f / 8, 1.f / 16, 1.f / 32, 1.f / 64, 1.f / 128, 1.f / 256};
+                float *row = reinterpret_cast<float *>(p.out) + frame * p.pitch;
+                float mx = 0.0f;
+                int idx = 0;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    float m = acc[b] * p.band_scale * (OUT == OUT_BANDS_LOG ? inv_log[b] : (1.0f / 3.0f));
+                    row[b] = m;
+                    if (m > mx) { mx = m; idx = b; }           // examples/pong/main.rs:200-207
+                }
+                row[8] = (float)idx;
+                row[9] = mx;
+            }
+        } else {
+            if (l == 0) emit_at<OUT, WIN>(o_lo + (M / 2) * EB, make_float2(2.0f * d0[4].x, -2.0f * d0[4].y));
+        }
         __syncwarp();
     }
 }

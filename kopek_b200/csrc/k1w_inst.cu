@@ -95,7 +95,11 @@ cudaError_t k1w_launch(const K1WParams &p, int output, bool win, int variant, in
         case 4: return launch_o<OUT_POWER, false>(p, variant, grid, stream, occ_out);
         case 5: return launch_o<OUT_POWER, true>(p, variant, grid, stream, occ_out);
         case 6: return launch_o<OUT_DB, false>(p, variant, grid, stream, occ_out);
-        default: return launch_o<OUT_DB, true>(p, variant, grid, stream, occ_out);
+        case 7: return launch_o<OUT_DB, true>(p, variant, grid, stream, occ_out);
+        case 8: return launch_o<OUT_BANDS_LOG, false>(p, variant, grid, stream, occ_out);
+        case 9: return launch_o<OUT_BANDS_LOG, true>(p, variant, grid, stream, occ_out);
+        case 10: return launch_o<OUT_BANDS_LOW, false>(p, variant, grid, stream, occ_out);
+        default: return launch_o<OUT_BANDS_LOW, true>(p, variant, grid, stream, occ_out);
     }
 }
 

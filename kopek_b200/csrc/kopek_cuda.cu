@@ -232,6 +232,7 @@ struct kopek_plan {
     float2 *d_tw, *d_pw;
     float4 *d_k1w;     // tables of the warp-per-frame kernel (n == 1024 only)
     int k1w_variant, k1w_warps_per_sm;
+    float band_scale;
     mutable uint32_t last_launches;
     // exec_host resources (lazy)
     std::mutex mu;
@@ -372,9 +373,14 @@ kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint
     }
     if (hop == 0) return fail(KOPEK_ERR_INVALID, "hop must be >= 1");
     if (window > KOPEK_WINDOW_CUSTOM) return fail(KOPEK_ERR_INVALID, "unknown window %u", window);
-    if (output > KOPEK_OUT_DB) return fail(KOPEK_ERR_INVALID, "unknown output %u", output);
+    if (output > KOPEK_OUT_BANDS_LOW) return fail(KOPEK_ERR_INVALID, "unknown output %u", output);
+    const bool bands = output >= KOPEK_OUT_BANDS_LOG;
+    if (bands && (n != 1024 || bins != KOPEK_BINS_HALF))
+        return fail(KOPEK_ERR_UNSUPPORTED, "band epilogues need n = 1024 and KOPEK_BINS_HALF (the reference's callers "
+                                           "analyse 1024-sample frames)");
+    if (bands && hop % 4 != 0) return fail(KOPEK_ERR_UNSUPPORTED, "band epilogues need hop %% 4 == 0");
     if (bins > KOPEK_BINS_FULL) return fail(KOPEK_ERR_INVALID, "unknown bins mode %u", bins);
-    const uint64_t nb = bins == KOPEK_BINS_FULL ? n : n / 2 + 1;
+    const uint64_t nb = bands ? KOPEK_BAND_ROW : bins == KOPEK_BINS_FULL ? n : n / 2 + 1;
     if (out_pitch_elems == 0) out_pitch_elems = nb;
     if (out_pitch_elems < nb) return fail(KOPEK_ERR_INVALID, "out_pitch_elems %llu < bins per frame %llu",
                                           (unsigned long long)out_pitch_elems, (unsigned long long)nb);
@@ -391,7 +397,7 @@ kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint
     p->bins = nb; p->pitch = out_pitch_elems; p->elem_bytes = output == KOPEK_OUT_COMPLEX ? 8 : 4;
     p->device = device; p->launch = launch; p->info = info();
     p->d_win = nullptr; p->d_tw = nullptr; p->d_pw = nullptr; p->last_launches = 0; p->slot_frames = 0;
-    p->d_k1w = nullptr; p->k1w_variant = 0; p->k1w_warps_per_sm = 0;
+    p->d_k1w = nullptr; p->k1w_variant = 0; p->k1w_warps_per_sm = 0; p->band_scale = 1.0f;
 
     kopek_status st = KOPEK_OK;
     do {
@@ -404,7 +410,7 @@ kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint
             break;
         }
         p->sm_count = prop.multiProcessorCount;
-        p->occupancy = occ((int)output, window != KOPEK_WINDOW_RECT);
+        p->occupancy = occ(bands ? (int)KOPEK_OUT_MAG : (int)output, window != KOPEK_WINDOW_RECT);
         if (p->occupancy <= 0) { st = fail(KOPEK_ERR_CUDA, "kernel for n=%u cannot be resident: %s", n,
                                            cudaGetErrorString(cudaGetLastError())); break; }
         const uint32_t M = n / 2;
@@ -432,7 +438,8 @@ kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint
             // headline size: warp-per-frame kernel (fft_warp1024.cuh); K1 stays for FULL bins / odd hops
             const char *env = getenv("KOPEK_K1W_VARIANT");
             p->k1w_variant = env ? atoi(env) : 0;
-            if (p->k1w_variant >= 0) {
+            if (p->k1w_variant >= 0 || bands) {
+                if (p->k1w_variant < 0) p->k1w_variant = 0;
                 std::vector<float4> t(K1W_TABLE_F4);
                 k1w_build_tables(nullptr, t.data());
                 if ((e = cudaMalloc(&p->d_k1w, sizeof(float4) * K1W_TABLE_F4)) != cudaSuccess ||
@@ -468,6 +475,12 @@ kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint
     return KOPEK_OK;
 }
 
+kopek_status kopek_plan_set_band_scale(kopek_plan *plan, float scale) {
+    if (!plan) return fail(KOPEK_ERR_INVALID, "plan is NULL");
+    plan->band_scale = scale;
+    return KOPEK_OK;
+}
+
 kopek_status kopek_plan_set_window(kopek_plan *plan, const float *window_host) {
     if (!plan || !window_host) return fail(KOPEK_ERR_INVALID, "NULL argument");
     if (plan->window != KOPEK_WINDOW_CUSTOM)
@@ -498,6 +511,8 @@ uint32_t kopek_plan_last_launches(const kopek_plan *plan) { return plan ? plan->
 
 static kopek_status stft_launch(const kopek_plan *plan, const float *d_samples, uint64_t frames, void *d_out,
                                 cudaStream_t stream) {
+    if (plan->output >= KOPEK_OUT_BANDS_LOG && (uintptr_t)d_samples % 16 != 0)
+        return fail(KOPEK_ERR_INVALID, "band epilogues need a 16-byte aligned sample buffer");
     if (plan->d_k1w && plan->bins_mode == KOPEK_BINS_HALF && plan->hop % 4 == 0 && (uintptr_t)d_samples % 16 == 0) {
         K1WParams wp;
         wp.x = d_samples;
@@ -506,6 +521,7 @@ static kopek_status stft_launch(const kopek_plan *plan, const float *d_samples, 
         wp.n_frames = frames;
         wp.hop = plan->hop;
         wp.pitch = plan->pitch;
+        wp.band_scale = plan->band_scale;
         const uint64_t warps = (uint64_t)plan->sm_count * plan->k1w_warps_per_sm;
         const int wpb = k1w_variant_warps(plan->k1w_variant);
         const int grid = (int)std::min<uint64_t>((frames + wpb - 1) / wpb, warps / wpb);

@@ -18,12 +18,13 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (BINS_FULL, BINS_HALF, OUT_COMPLEX, OUT_DB, OUT_MAG, OUT_POWER, WINDOW_CUSTOM, WINDOW_HAMMING,
+from ._lib import (BAND_ROW, BINS_FULL, BINS_HALF, OUT_BANDS_LOG, OUT_BANDS_LOW, OUT_COMPLEX, OUT_DB, OUT_MAG, OUT_POWER, WINDOW_CUSTOM, WINDOW_HAMMING,
                    WINDOW_HANN, WINDOW_RECT, KopekError, check)
 
 __all__ = ["fft", "fft_batched", "fft_large_device", "show", "show_format", "StftPlan", "next_pow2", "KopekError",
            "WINDOW_RECT", "WINDOW_HANN", "WINDOW_HAMMING", "WINDOW_CUSTOM",
-           "OUT_COMPLEX", "OUT_MAG", "OUT_POWER", "OUT_DB", "BINS_HALF", "BINS_FULL"]
+           "OUT_COMPLEX", "OUT_MAG", "OUT_POWER", "OUT_DB", "OUT_BANDS_LOG", "OUT_BANDS_LOW", "BAND_ROW",
+           "BINS_HALF", "BINS_FULL"]
 
 
 def next_pow2(n: int) -> int:
@@ -74,7 +75,8 @@ class StftPlan:
     """Fused window -> real FFT -> |X|/dB plan (kopek_plan_* / kopek_stft_exec*)."""
 
     def __init__(self, n: int, hop: int | None = None, window: int = WINDOW_RECT, output: int = OUT_MAG,
-                 bins: int = BINS_HALF, out_pitch: int = 0, device: int = 0, custom_window=None):
+                 bins: int = BINS_HALF, out_pitch: int = 0, device: int = 0, custom_window=None,
+                 band_scale: float | None = None):
         self._h = C.c_void_p()
         self._lib = _lib.load()
         hop = n if hop is None else hop
@@ -83,6 +85,8 @@ class StftPlan:
         self.bins = int(self._lib.kopek_plan_bins(self._h))
         self.pitch = int(self._lib.kopek_plan_out_pitch(self._h))
         self.elem_bytes = int(self._lib.kopek_plan_out_elem_bytes(self._h))
+        if band_scale is not None:
+            check(self._lib.kopek_plan_set_band_scale(self._h, band_scale))
         if custom_window is not None:
             w = np.ascontiguousarray(custom_window, dtype=np.float32)
             if w.size != n:
