@@ -54,7 +54,7 @@ __device__ __forceinline__ void k3_stage(float2 *buf, const float2 *tw, int tid,
             if constexpr (TILE_MAJOR_IN) pos = ((q >> 2) << 4) + (c << 2) + (q & 3);   // [q/4][c][q%4]
             else pos = (READ_LINEAR ? q : k3_swz(q)) * 4 + c;
             float2 v = buf[pos];
-            if (NS > 1 && t > 0) v = cmul(v, tw[kk * t * (M / (NS * RAD))]);
+            if (NS > 1 && t > 0) v = cmul(v, __ldg(tw + (t - 1) * NS + kk));   // stage table, t-major
             d[i * RAD + t] = v;
         }
     }
@@ -83,7 +83,7 @@ __device__ __forceinline__ void k3_fft_tile(float2 *buf, const float2 *tw, int t
     if constexpr (C::R2 > 1) {
         k3_stage<C::R0, 1, M, T, true, false, TILE_MAJOR_IN>(buf, tw, tid, c);
         k3_stage<C::R1, C::R0, M, T, false, false, false>(buf, tw, tid, c);
-        k3_stage<C::R2, C::R0 * C::R1, M, T, false, true, false>(buf, tw, tid, c);
+        k3_stage<C::R2, C::R0 * C::R1, M, T, false, true, false>(buf, tw + (C::R1 - 1) * C::R0, tid, c);
     } else {
         k3_stage<C::R0, 1, M, T, true, false, TILE_MAJOR_IN>(buf, tw, tid, c);
         k3_stage<C::R1, C::R0, M, T, false, true, false>(buf, tw, tid, c);
@@ -104,8 +104,8 @@ __device__ __forceinline__ void tma_store_commit_wait() {
 }
 
 struct K3Tables {
-    const float2 *tw_sub1;   // W_N1^e, e < N1  (stage twiddles of pass 1)
-    const float2 *tw_sub2;   // W_N2^e, e < N2
+    const float2 *tw_sub1;   // per-stage t-major twiddles of the N1-point sub-transform (k3_stage_twiddles)
+    const float2 *tw_sub2;   // same for N2
     const float2 *tw_hi;     // W_n^{4096 h}, h < n/4096 (two-level inter-step twiddle)
     const float2 *tw_lo;     // W_n^{l},      l < 4096
 };
@@ -217,6 +217,32 @@ struct K3Plan {
 static std::mutex g_k3_mu;
 static std::vector<K3Plan> g_k3_plans;
 
+// Stage tables of the M-point Stockham sub-transform: block s holds tw[(t-1) NS + kk] = W_{NS RAD}^{kk t}.
+template <int M> static void stage_twiddles_t(std::vector<float2> &v) {
+    using C = K3Cfg<M>;
+    v.assign(M, make_float2(1.0f, 0.0f));
+    const int rad[2] = {C::R1, C::R2}, ns[2] = {C::R0, C::R0 * C::R1};
+    int off = 0;
+    for (int s = 0; s < 2; ++s) {
+        if (rad[s] <= 1) break;
+        for (int t = 1; t < rad[s]; ++t)
+            for (int kk = 0; kk < ns[s]; ++kk) {
+                double th = -2.0 * M_PI * (double)(kk * t) / (double)(ns[s] * rad[s]);
+                v[off + (t - 1) * ns[s] + kk] = make_float2((float)cos(th), (float)sin(th));
+            }
+        off += (rad[s] - 1) * ns[s];
+    }
+}
+static void k3_stage_twiddles(int m, std::vector<float2> &v) {
+    switch (m) {
+        case 256: stage_twiddles_t<256>(v); break;
+        case 512: stage_twiddles_t<512>(v); break;
+        case 1024: stage_twiddles_t<1024>(v); break;
+        case 2048: stage_twiddles_t<2048>(v); break;
+        default: stage_twiddles_t<4096>(v); break;
+    }
+}
+
 static void fill_twiddles(std::vector<float2> &v, uint64_t count, uint64_t step, uint64_t n) {
     v.resize(count);
     for (uint64_t i = 0; i < count; ++i) {
@@ -236,8 +262,8 @@ static kopek_status k3_get_plan(uint64_t n, int device, K3Plan *out) {
     p.n1 = 1 << (lg / 2);
     p.n2 = (int)(n / p.n1);
     std::vector<float2> t1, t2, hi, lo;
-    fill_twiddles(t1, p.n1, 1, p.n1);
-    fill_twiddles(t2, p.n2, 1, p.n2);
+    k3_stage_twiddles(p.n1, t1);
+    k3_stage_twiddles(p.n2, t2);
     fill_twiddles(hi, n / 4096, 4096, n);
     fill_twiddles(lo, 4096, 1, n);
     auto up = [](float2 **d, const std::vector<float2> &h) {
