@@ -123,10 +123,13 @@ __device__ __forceinline__ int band_low_of(int k) {
 // WINREG: so does the lane's slice of the window.
 // TMA: the NEXT frame of the warp is fetched by one cp.async.bulk into the warp's landing buffer while
 //      the current one is transformed (the buffer is free as soon as pass A has read it).
-template <int OUT, bool WIN, int WARPS, int MINB, bool TWREG, bool WINREG, bool TMA>
+// LOAD: 0 = plain LDG.128 at the top of the frame, 1 = TMA prefetch (above), 2 = LDG.128 of the next frame
+//       into registers at the top of the current one (no shared-memory landing traffic, 32 more registers).
+template <int OUT, bool WIN, int WARPS, int MINB, bool TWREG, bool WINREG, int LOAD>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 k1w_1024_kernel(const K1WParams p) {
     constexpr int M = 512;
+    constexpr bool TMA = LOAD == 1;
     extern __shared__ __align__(16) unsigned char k1w_smem[];
     float4 *s_win = reinterpret_cast<float4 *>(k1w_smem);
     float4 *s_tpp = s_win + K1W_WIN_F4;
@@ -183,10 +186,26 @@ k1w_1024_kernel(const K1WParams p) {
         }
         __syncwarp();
     }
+    float4 vn[8];                                            // LOAD == 2: the next frame, in flight
+    if constexpr (LOAD == 2) {
+        if (first < p.n_frames) {
+            const float4 *xf = reinterpret_cast<const float4 *>(p.x + first * p.hop) + l;
+#pragma unroll
+            for (int n2 = 0; n2 < 8; ++n2) vn[n2] = ldg_stream(xf + 32 * n2);
+        }
+    }
     for (uint64_t frame = first; frame < p.n_frames; frame += total_warps) {
         // ---- A: load + window, transform over n2, twiddle, publish
         float4 v[8];
-        if constexpr (TMA) {
+        if constexpr (LOAD == 2) {
+#pragma unroll
+            for (int n2 = 0; n2 < 8; ++n2) v[n2] = vn[n2];
+            if (frame + total_warps < p.n_frames) {
+                const float4 *xf = reinterpret_cast<const float4 *>(p.x + (frame + total_warps) * p.hop) + l;
+#pragma unroll
+                for (int n2 = 0; n2 < 8; ++n2) vn[n2] = ldg_stream(xf + 32 * n2);
+            }
+        } else if constexpr (TMA) {
             mbar_wait(bar, phase);
             phase ^= 1;
 #pragma unroll

@@ -35,10 +35,10 @@ void k1w_build_tables(const float *half_window /* 1024 or nullptr */, float4 *ou
         }
 }
 
-template <int OUT, bool WIN, int WARPS, int MINB, bool TWREG, bool WINREG, bool TMA>
+template <int OUT, bool WIN, int WARPS, int MINB, bool TWREG, bool WINREG, int LOAD>
 static cudaError_t launch_v(const K1WParams &p, int grid, cudaStream_t stream, int *occ_out) {
-    using G = K1WGeom<WARPS, TMA>;
-    auto kern = k1w_1024_kernel<OUT, WIN, WARPS, MINB, TWREG, WINREG, TMA>;
+    using G = K1WGeom<WARPS, LOAD == 1>;
+    auto kern = k1w_1024_kernel<OUT, WIN, WARPS, MINB, TWREG, WINREG, LOAD>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
     if (e != cudaSuccess) return e;
     if (occ_out) {
@@ -51,23 +51,24 @@ static cudaError_t launch_v(const K1WParams &p, int grid, cudaStream_t stream, i
     return cudaGetLastError();
 }
 
-// variant table: (warps per CTA, min CTAs per SM, twiddles in registers, window in registers, TMA prefetch).
-// Variant 0 is the production configuration (measured best on B200, profiles/r1_k1w_sweep.md); the others
-// are only compiled with -DKOPEK_K1W_SWEEP for tools/sweep_k1w.py.
+// variant table: (warps per CTA, min CTAs per SM, twiddles in registers, window in registers, load mode:
+// 0 LDG, 1 TMA prefetch, 2 LDG register prefetch).  Variant 0 is the production configuration (measured best
+// on B200, profiles/r1_k1w_sweep.md); the others are only compiled with -DKOPEK_K1W_SWEEP for tools/sweep_k1w.py.
 #ifdef KOPEK_K1W_SWEEP
 #define KOPEK_K1W_VARIANTS(X)                                                                      \
-    X(0, 4, 3, true, true, true) X(1, 8, 3, false, false, true) X(2, 4, 6, true, false, true)      \
-    X(3, 4, 5, true, false, true) X(4, 4, 4, true, false, true) X(5, 4, 4, true, true, true)       \
-    X(6, 8, 2, true, true, true) X(7, 4, 6, true, false, false) X(8, 4, 5, false, true, true)      \
-    X(9, 4, 4, false, true, true) X(10, 8, 2, false, true, true) X(11, 4, 5, false, false, true)   \
-    X(12, 2, 6, true, true, true) X(13, 4, 6, false, false, false) X(14, 2, 7, true, true, true)   \
-    X(15, 1, 12, true, true, true) X(16, 6, 2, true, true, true) X(17, 2, 8, true, true, true)
+    X(0, 4, 3, true, true, 1) X(1, 4, 2, true, true, 2) X(2, 4, 3, true, true, 2)                  \
+    X(3, 4, 2, true, true, 1) X(4, 4, 4, true, true, 1) X(5, 4, 4, true, false, 2)                 \
+    X(6, 2, 5, true, true, 2) X(7, 2, 6, true, true, 1) X(8, 4, 3, true, false, 2)                 \
+    X(9, 4, 3, true, true, 0)
 #else
-#define KOPEK_K1W_VARIANTS(X) X(0, 4, 3, true, true, true)
+#define KOPEK_K1W_VARIANTS(X) X(0, 4, 3, true, true, 1)
 #endif
+// Variant 0 without a window has 32 registers to spare: the next frame is prefetched into registers
+// (LOAD 2: 93 % of the roofline vs 88.5 % with the TMA landing buffer, profiles/r1_k1w_sweep.md).
 
 template <int OUT, bool WIN>
 static cudaError_t launch_o(const K1WParams &p, int variant, int grid, cudaStream_t stream, int *occ_out) {
+    if (variant == 0 && !WIN) return launch_v<OUT, WIN, 4, 3, true, true, 2>(p, grid, stream, occ_out);
     switch (variant) {
 #define X(ID, W, B, T, R, A) case ID: return launch_v<OUT, WIN, W, B, T, R, A>(p, grid, stream, occ_out);
         KOPEK_K1W_VARIANTS(X)
