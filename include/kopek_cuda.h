@@ -126,6 +126,19 @@ KOPEK_API kopek_status kopek_stft_exec_host(kopek_plan *plan, const float *h_sam
 KOPEK_API kopek_status kopek_host_alloc(void **ptr, size_t bytes);   /* page-locked host memory */
 KOPEK_API kopek_status kopek_host_free(void *ptr);
 
+/* ---- 2b. live sliding window (examples/beep/view.rs:44,57-60,140-158) -----------------------
+ * The beep view keeps the most recent 1024 samples in a VecDeque (new samples pushed at the back, old
+ * ones popped at the front) and transforms the whole deque once per UI frame.  A kopek_stream is that
+ * deque on the device: push() appends `count` new host samples (history starts as zeros), then writes
+ * the spectrum of the most recent n samples to h_out (kopek_stream_bins() elements, f32 or (re,im) f32).
+ * input_scale multiplies every sample before the transform (1/32767 in beep/view.rs:143, 1 in pong). */
+typedef struct kopek_stream kopek_stream;
+KOPEK_API kopek_status kopek_stream_create(kopek_stream **stream, uint32_t n, uint32_t window, uint32_t output,
+                                           float input_scale, int device);
+KOPEK_API kopek_status kopek_stream_push(kopek_stream *stream, const float *h_samples, uint32_t count, void *h_out);
+KOPEK_API uint64_t kopek_stream_bins(const kopek_stream *stream);
+KOPEK_API kopek_status kopek_stream_destroy(kopek_stream *stream);
+
 /* ---- 3. large single transform (four-step), device-resident c2c f32 ----------
  * Interleaved (re,im) f32, n a power of two with 2^16 <= n <= 2^24, natural-order unnormalised
  * output, d_in != d_out, both 16-byte aligned.  Two HBM passes with TMA-staged tiles; asynchronous

@@ -10,6 +10,6 @@ Layout:
 from . import _lib  # noqa: F401
 from . import fft  # noqa: F401  -- kopek_b200.fft.fft / kopek_b200.fft.show mirror kopek::fft::{fft, show}
 from .fft import (BAND_ROW, BINS_FULL, BINS_HALF, OUT_BANDS_LOG, OUT_BANDS_LOW, OUT_COMPLEX, OUT_DB, OUT_MAG, OUT_POWER, WINDOW_CUSTOM, WINDOW_HAMMING,
-                  WINDOW_HANN, WINDOW_RECT, KopekError, StftPlan)
+                  WINDOW_HANN, WINDOW_RECT, KopekError, LiveSpectrum, StftPlan)
 
 __version__ = "0.1.0"

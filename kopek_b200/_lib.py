@@ -41,6 +41,10 @@ SYMBOLS = {
     "kopek_plan_last_launches": (_u32, [_vp]),
     "kopek_stft_exec": (_i32, [_vp, _vp, _u64, _vp, C.POINTER(_u64), _vp]),
     "kopek_stft_exec_host": (_i32, [_vp, _vp, _u64, _vp, C.POINTER(_u64)]),
+    "kopek_stream_create": (_i32, [C.POINTER(_vp), _u32, _u32, _u32, C.c_float, C.c_int]),
+    "kopek_stream_push": (_i32, [_vp, _vp, _u32, _vp]),
+    "kopek_stream_bins": (_u64, [_vp]),
+    "kopek_stream_destroy": (_i32, [_vp]),
     "kopek_host_alloc": (_i32, [C.POINTER(_vp), _sz]),
     "kopek_host_free": (_i32, [_vp]),
     "kopek_fft_large_c2c_f32": (_i32, [_vp, _vp, _u64, C.c_int, _vp]),

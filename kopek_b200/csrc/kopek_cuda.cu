@@ -620,6 +620,108 @@ kopek_status kopek_stft_exec_host(kopek_plan *plan, const float *h_samples, uint
     return KOPEK_OK;
 }
 
+// ------------------------------------------------------------- live stream ----
+struct kopek_stream {
+    kopek_plan *plan;
+    uint32_t n;
+    int device;
+    uint64_t written;          // total samples pushed so far
+    float *d_ring;             // 2n floats: sample i lives at i % n and i % n + n
+    float *h_in;               // pinned staging, n floats
+    void *h_out;               // pinned staging, one spectrum
+    void *d_out;
+    cudaStream_t cs;
+    std::mutex mu;
+};
+
+kopek_status kopek_stream_create(kopek_stream **stream, uint32_t n, uint32_t window, uint32_t output,
+                                 float input_scale, int device) {
+    if (!stream) return fail(KOPEK_ERR_INVALID, "stream is NULL");
+    *stream = nullptr;
+    if (window > KOPEK_WINDOW_HAMMING) return fail(KOPEK_ERR_INVALID, "stream window must be RECT, HANN or HAMMING");
+    // the scale rides on the window table (exactly one f32 product per sample, like w[i] * x[i])
+    const bool scaled = input_scale != 1.0f;
+    kopek_plan *plan = nullptr;
+    kopek_status st = kopek_plan_create(&plan, n, n, scaled ? (uint32_t)KOPEK_WINDOW_CUSTOM : window, output,
+                                        KOPEK_BINS_HALF, 0, device);
+    if (st != KOPEK_OK) return st;
+    if (scaled) {
+        std::vector<float> w;
+        host_window(window, n, w);
+        for (float &v : w) v = (float)((double)v * (double)input_scale);
+        st = kopek_plan_set_window(plan, w.data());
+        if (st != KOPEK_OK) { kopek_plan_destroy(plan); return st; }
+    }
+    kopek_stream *s = new (std::nothrow) kopek_stream();
+    if (!s) { kopek_plan_destroy(plan); return fail(KOPEK_ERR_NOMEM, "out of host memory"); }
+    s->plan = plan; s->n = n; s->device = device; s->written = 0;
+    s->d_ring = nullptr; s->h_in = nullptr; s->h_out = nullptr; s->d_out = nullptr; s->cs = nullptr;
+    DeviceGuard g(device);
+    const size_t ob = plan->bins * plan->elem_bytes;
+    cudaError_t e;
+    if ((e = cudaMalloc(&s->d_ring, 2 * n * sizeof(float))) != cudaSuccess ||
+        (e = cudaMemset(s->d_ring, 0, 2 * n * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc(&s->d_out, ob)) != cudaSuccess ||
+        (e = cudaMallocHost(&s->h_in, n * sizeof(float))) != cudaSuccess ||
+        (e = cudaMallocHost(&s->h_out, ob)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&s->cs, cudaStreamNonBlocking)) != cudaSuccess) {
+        kopek_stream_destroy(s);
+        return fail(KOPEK_ERR_CUDA, "stream setup failed: %s", cudaGetErrorString(e));
+    }
+    *stream = s;
+    return KOPEK_OK;
+}
+
+uint64_t kopek_stream_bins(const kopek_stream *stream) { return stream ? stream->plan->bins : 0; }
+
+kopek_status kopek_stream_push(kopek_stream *s, const float *h_samples, uint32_t count, void *h_out) {
+    if (!s || !h_out || (count && !h_samples)) return fail(KOPEK_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    DeviceGuard g(s->device);
+    if (!g.ok) return fail(KOPEK_ERR_CUDA, "cannot select device %d", s->device);
+    const uint32_t n = s->n;
+    if (count > n) {                       // only the last n samples can survive in the window
+        s->written += count - n;
+        h_samples += count - n;
+        count = n;
+    }
+    if (count) {
+        memcpy(s->h_in, h_samples, count * sizeof(float));
+        uint32_t pos = (uint32_t)(s->written % n), done = 0;
+        while (done < count) {             // at most two segments (wrap), each written to both ring halves
+            uint32_t seg = std::min(count - done, n - pos);
+            KOPEK_CUDA(cudaMemcpyAsync(s->d_ring + pos, s->h_in + done, seg * sizeof(float), cudaMemcpyHostToDevice, s->cs));
+            KOPEK_CUDA(cudaMemcpyAsync(s->d_ring + pos + n, s->h_in + done, seg * sizeof(float), cudaMemcpyHostToDevice, s->cs));
+            done += seg;
+            pos = (pos + seg) % n;
+        }
+        s->written += count;
+    }
+    // the most recent n samples are contiguous from (written % n) in the doubled ring
+    const float *frame = s->d_ring + (s->written % n);
+    uint64_t nf = 0;
+    kopek_status st = kopek_stft_exec(s->plan, frame, n, s->d_out, &nf, s->cs);
+    if (st != KOPEK_OK) return st;
+    const size_t ob = s->plan->bins * s->plan->elem_bytes;
+    KOPEK_CUDA(cudaMemcpyAsync(s->h_out, s->d_out, ob, cudaMemcpyDeviceToHost, s->cs));
+    KOPEK_CUDA(cudaStreamSynchronize(s->cs));
+    memcpy(h_out, s->h_out, ob);
+    return KOPEK_OK;
+}
+
+kopek_status kopek_stream_destroy(kopek_stream *s) {
+    if (!s) return KOPEK_OK;
+    DeviceGuard g(s->device);
+    if (s->cs) { cudaStreamSynchronize(s->cs); cudaStreamDestroy(s->cs); }
+    if (s->d_ring) cudaFree(s->d_ring);
+    if (s->d_out) cudaFree(s->d_out);
+    if (s->h_in) cudaFreeHost(s->h_in);
+    if (s->h_out) cudaFreeHost(s->h_out);
+    if (s->plan) kopek_plan_destroy(s->plan);
+    delete s;
+    return KOPEK_OK;
+}
+
 kopek_status kopek_host_alloc(void **ptr, size_t bytes) {
     if (!ptr) return fail(KOPEK_ERR_INVALID, "ptr is NULL");
     *ptr = nullptr;

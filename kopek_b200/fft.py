@@ -21,7 +21,7 @@ from . import _lib
 from ._lib import (BAND_ROW, BINS_FULL, BINS_HALF, OUT_BANDS_LOG, OUT_BANDS_LOW, OUT_COMPLEX, OUT_DB, OUT_MAG, OUT_POWER, WINDOW_CUSTOM, WINDOW_HAMMING,
                    WINDOW_HANN, WINDOW_RECT, KopekError, check)
 
-__all__ = ["fft", "fft_batched", "fft_large_device", "show", "show_format", "StftPlan", "next_pow2", "KopekError",
+__all__ = ["fft", "fft_batched", "fft_large_device", "LiveSpectrum", "show", "show_format", "StftPlan", "next_pow2", "KopekError",
            "WINDOW_RECT", "WINDOW_HANN", "WINDOW_HAMMING", "WINDOW_CUSTOM",
            "OUT_COMPLEX", "OUT_MAG", "OUT_POWER", "OUT_DB", "OUT_BANDS_LOG", "OUT_BANDS_LOW", "BAND_ROW",
            "BINS_HALF", "BINS_FULL"]
@@ -140,3 +140,34 @@ class StftPlan:
 
     def __exit__(self, *exc):
         self.close()
+
+
+class LiveSpectrum:
+    """Sliding-window analyser of the live examples (kopek_stream_*): the VecDeque of the most recent n samples
+    of examples/beep/view.rs:44,57-60 kept on the device; `push(new_samples)` returns the spectrum of the
+    window that ends at the newest sample (history starts as zeros)."""
+
+    def __init__(self, n: int = 1024, window: int = WINDOW_RECT, output: int = OUT_MAG, input_scale: float = 1.0,
+                 device: int = 0):
+        self._h = C.c_void_p()
+        self._lib = _lib.load()
+        check(self._lib.kopek_stream_create(C.byref(self._h), n, window, output, input_scale, device))
+        self.n, self.output = n, output
+        self.bins = int(self._lib.kopek_stream_bins(self._h))
+
+    def push(self, samples) -> np.ndarray:
+        s = np.ascontiguousarray(samples, dtype=np.float32).reshape(-1)
+        out = np.empty(self.bins, dtype=np.complex64 if self.output == OUT_COMPLEX else np.float32)
+        check(self._lib.kopek_stream_push(self._h, s.ctypes.data if s.size else None, s.size, out.ctypes.data))
+        return out
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.kopek_stream_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
