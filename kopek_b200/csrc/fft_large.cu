@@ -39,8 +39,11 @@ __host__ __device__ constexpr int k3_swz(int q) { return q ^ ((q >> 4) & 15); }
 // One Stockham stage on 4 interleaved columns: element (q, c) lives at buf[pos(q) * 4 + c].
 // READ_LINEAR / WRITE_LINEAR select the dense layout TMA produced / consumes; otherwise the swizzled one.
 // FIRST_MAP remaps the logical index of the very first read (pass 2: tile-major block order).
-template <int RAD, int NS, int M, int T, bool READ_LINEAR, bool WRITE_LINEAR, bool TILE_MAJOR_IN>
-__device__ __forceinline__ void k3_stage(float2 *buf, const float2 *tw, int tid, int c) {
+// XTW (last stage of pass 1 only): the inter-step twiddle W_n^{n2 q} is applied to output q in registers just
+// before the final write (two-level table: W^m = W^{4096 (m >> 12)} W^{m & 4095}), saving a pass over the tile.
+template <int RAD, int NS, int M, int T, bool READ_LINEAR, bool WRITE_LINEAR, bool TILE_MAJOR_IN, bool XTW = false>
+__device__ __forceinline__ void k3_stage(float2 *buf, const float2 *tw, int tid, int c, uint32_t n2 = 0,
+                                         const float2 *tw_hi = nullptr, const float2 *tw_lo = nullptr) {
     constexpr int NB = 16 / RAD;
     float2 d[16];
 #pragma unroll
@@ -69,24 +72,31 @@ __device__ __forceinline__ void k3_stage(float2 *buf, const float2 *tw, int tid,
 #pragma unroll
         for (int k = 0; k < RAD; ++k) {
             int q = base + k * NS;
-            buf[(WRITE_LINEAR ? q : k3_swz(q)) * 4 + c] = d[i * RAD + k];
+            float2 v = d[i * RAD + k];
+            if constexpr (XTW) {
+                uint32_t m = n2 * (uint32_t)q;
+                v = cmul(v, cmul(__ldg(tw_hi + (m >> 12)), __ldg(tw_lo + (m & 4095u))));
+            }
+            buf[(WRITE_LINEAR ? q : k3_swz(q)) * 4 + c] = v;
         }
     }
     __syncthreads();
 }
 
 // M-point FFT of the 4 interleaved columns in `buf`; result dense: buf[k * 4 + c].
-template <int M, bool TILE_MAJOR_IN>
-__device__ __forceinline__ void k3_fft_tile(float2 *buf, const float2 *tw, int tid, int c) {
+template <int M, bool TILE_MAJOR_IN, bool XTW>
+__device__ __forceinline__ void k3_fft_tile(float2 *buf, const float2 *tw, int tid, int c, uint32_t n2 = 0,
+                                            const float2 *tw_hi = nullptr, const float2 *tw_lo = nullptr) {
     using C = K3Cfg<M>;
     constexpr int T = M / 16;
     if constexpr (C::R2 > 1) {
         k3_stage<C::R0, 1, M, T, true, false, TILE_MAJOR_IN>(buf, tw, tid, c);
         k3_stage<C::R1, C::R0, M, T, false, false, false>(buf, tw, tid, c);
-        k3_stage<C::R2, C::R0 * C::R1, M, T, false, true, false>(buf, tw + (C::R1 - 1) * C::R0, tid, c);
+        k3_stage<C::R2, C::R0 * C::R1, M, T, false, true, false, XTW>(buf, tw + (C::R1 - 1) * C::R0, tid, c, n2, tw_hi,
+                                                                       tw_lo);
     } else {
         k3_stage<C::R0, 1, M, T, true, false, TILE_MAJOR_IN>(buf, tw, tid, c);
-        k3_stage<C::R1, C::R0, M, T, false, true, false>(buf, tw, tid, c);
+        k3_stage<C::R1, C::R0, M, T, false, true, false, XTW>(buf, tw, tid, c, n2, tw_hi, tw_lo);
     }
 }
 
@@ -110,70 +120,128 @@ struct K3Tables {
     const float2 *tw_lo;     // W_n^{l},      l < 4096
 };
 
-// ---- pass 1: column tile s = blockIdx.x (columns 4s..4s+3), all n1
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+
+// Both passes are PERSISTENT: one CTA per SM loops over its tiles.  The tile buffer is a ring of
+// 256-row boxes: each box is stored with its own bulk group, and as soon as the TMA engine has read
+// box b out of shared memory (wait_group.read) the same box of the NEXT tile is loaded into it, so the
+// store of tile i and the load of tile i+1 overlap (only the FFT itself is not overlapped with memory).
+
+// ---- pass 1: column tiles s (columns 4s..4s+3), all n1
 template <int N1>
 __global__ void __launch_bounds__(N1 / 4, 1)
-k3_pass1(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap mid_map, K3Tables tb) {
+k3_pass1(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap mid_map, K3Tables tb,
+         int n_tiles) {
     extern __shared__ __align__(128) unsigned char k3_smem[];
     float2 *buf = reinterpret_cast<float2 *>(k3_smem);                 // N1 x 4 complex, dense
     uint64_t *bar = reinterpret_cast<uint64_t *>(k3_smem + (size_t)N1 * 32);
-    const int s = blockIdx.x;
+    constexpr int NBOX = N1 >= 1024 ? N1 / 1024 : 1;                   // load/store granule: 1024 rows = 32 KB
+    constexpr int BOX_ROWS = N1 / NBOX;
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(bar, N1 * 32);
-        for (int r0 = 0; r0 < N1; r0 += 256) tma_load_2d(buf + r0 * 4, &in_map, 8 * s, r0, bar);
+        if ((int)blockIdx.x < n_tiles) {
+            mbar_expect_tx(bar, N1 * 32);
+            for (int r0 = 0; r0 < N1; r0 += 256) tma_load_2d(buf + r0 * 4, &in_map, 8 * blockIdx.x, r0, bar);
+        }
     }
     __syncthreads();
-    mbar_wait(bar, 0);
     const int c = threadIdx.x & 3, tid = threadIdx.x >> 2;
-    k3_fft_tile<N1, false>(buf, tb.tw_sub1, tid, c);
-    // inter-step twiddle W_n^{n2 k1}, n2 = 4s + c; m = n2 k1 < n <= 2^24: W^m = W^{4096 (m>>12)} W^{m & 4095}
-    const uint32_t n2 = 4u * s + c;
-#pragma unroll 4
-    for (int k1 = tid; k1 < N1; k1 += N1 / 16) {
-        uint32_t m = n2 * (uint32_t)k1;
-        float2 w = cmul(__ldg(tb.tw_hi + (m >> 12)), __ldg(tb.tw_lo + (m & 4095u)));
-        buf[k1 * 4 + c] = cmul(buf[k1 * 4 + c], w);
+    uint32_t phase = 0;
+    for (int s = blockIdx.x; s < n_tiles; s += gridDim.x) {
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        // sub-transform + inter-step twiddle W_n^{n2 k1}, n2 = 4s + c (fused into the last stage's write)
+        k3_fft_tile<N1, false, true>(buf, tb.tw_sub1, tid, c, 4u * s + c, tb.tw_hi, tb.tw_lo);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic writes -> TMA store reads
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            // buf is [k1][c] dense = rows u = k1/4 of 16 complex (32 floats): the 128-byte segments of mid
+#pragma unroll
+            for (int b = 0; b < NBOX; ++b) {
+                for (int u0 = b * (BOX_ROWS / 4); u0 < (b + 1) * (BOX_ROWS / 4); u0 += 256)
+                    tma_store_2d(&mid_map, 32 * s, u0, buf + u0 * 16);
+                tma_store_commit();
+            }
+            const int nxt = s + gridDim.x;
+            if (nxt < n_tiles) mbar_expect_tx(bar, N1 * 32);
+#pragma unroll
+            for (int b = 0; b < NBOX; ++b) {
+                // box b has left shared memory once at most NBOX-1-b younger groups are still reading
+                switch (NBOX - 1 - b) {
+                    case 0: tma_store_wait_read<0>(); break;
+                    case 1: tma_store_wait_read<1>(); break;
+                    case 2: tma_store_wait_read<2>(); break;
+                    default: tma_store_wait_read<3>(); break;
+                }
+                if (nxt < n_tiles)
+                    for (int r0 = b * BOX_ROWS; r0 < (b + 1) * BOX_ROWS; r0 += 256)
+                        tma_load_2d(buf + r0 * 4, &in_map, 8 * nxt, r0, bar);
+            }
+        }
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic writes -> TMA store reads
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        // buf is [k1][c] dense = rows u = k1/4 of 16 complex (32 floats): the 128-byte segments of mid
-        for (int u0 = 0; u0 < N1 / 4; u0 += 256) tma_store_2d(&mid_map, 32 * s, u0, buf + u0 * 16);
-        tma_store_commit_wait();
-    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-// ---- pass 2: row tile u = blockIdx.x (rows k1 = 4u..4u+3), all n2; block mid[u] is contiguous
+// ---- pass 2: row tiles u (rows k1 = 4u..4u+3), all n2; block mid[u] is contiguous
 template <int N2>
 __global__ void __launch_bounds__(N2 / 4, 1)
-k3_pass2(const float2 *__restrict__ mid, const __grid_constant__ CUtensorMap out_map, K3Tables tb) {
+k3_pass2(const float2 *__restrict__ mid, const __grid_constant__ CUtensorMap out_map, K3Tables tb, int n_tiles) {
     extern __shared__ __align__(128) unsigned char k3_smem[];
     float2 *buf = reinterpret_cast<float2 *>(k3_smem);
     uint64_t *bar = reinterpret_cast<uint64_t *>(k3_smem + (size_t)N2 * 32);
-    const int u = blockIdx.x;
+    constexpr int NBOX = N2 >= 1024 ? N2 / 1024 : 1;
+    constexpr int BOX_ROWS = N2 / NBOX;
+    constexpr int CH = BOX_ROWS * 32 < 16384 ? BOX_ROWS * 32 : 16384;    // 1-D bulk copy granule
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(bar, N2 * 32);
-        const char *src = reinterpret_cast<const char *>(mid) + (size_t)u * N2 * 32;
-        constexpr int CH = N2 * 32 < 16384 ? N2 * 32 : 16384;
-        for (int off = 0; off < N2 * 32; off += CH) tma_load_1d(k3_smem + off, src + off, CH, bar);
+        if ((int)blockIdx.x < n_tiles) {
+            mbar_expect_tx(bar, N2 * 32);
+            const char *src = reinterpret_cast<const char *>(mid) + (size_t)blockIdx.x * N2 * 32;
+            for (int off = 0; off < N2 * 32; off += CH) tma_load_1d(k3_smem + off, src + off, CH, bar);
+        }
     }
     __syncthreads();
-    mbar_wait(bar, 0);
     const int c = threadIdx.x & 3, tid = threadIdx.x >> 2;
-    k3_fft_tile<N2, true>(buf, tb.tw_sub2, tid, c);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        // buf is [k2][c] dense; out is [k2][k1] with k1 = 4u + c: 32-byte rows
-        for (int r0 = 0; r0 < N2; r0 += 256) tma_store_2d(&out_map, 8 * u, r0, buf + r0 * 4);
-        tma_store_commit_wait();
+    uint32_t phase = 0;
+    for (int u = blockIdx.x; u < n_tiles; u += gridDim.x) {
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        k3_fft_tile<N2, true, false>(buf, tb.tw_sub2, tid, c);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            // buf is [k2][c] dense; out is [k2][k1] with k1 = 4u + c: 32-byte rows
+#pragma unroll
+            for (int b = 0; b < NBOX; ++b) {
+                for (int r0 = b * BOX_ROWS; r0 < (b + 1) * BOX_ROWS; r0 += 256)
+                    tma_store_2d(&out_map, 8 * u, r0, buf + r0 * 4);
+                tma_store_commit();
+            }
+            const int nxt = u + gridDim.x;
+            if (nxt < n_tiles) mbar_expect_tx(bar, N2 * 32);
+            const char *src = reinterpret_cast<const char *>(mid) + (size_t)nxt * N2 * 32;
+#pragma unroll
+            for (int b = 0; b < NBOX; ++b) {
+                switch (NBOX - 1 - b) {
+                    case 0: tma_store_wait_read<0>(); break;
+                    case 1: tma_store_wait_read<1>(); break;
+                    case 2: tma_store_wait_read<2>(); break;
+                    default: tma_store_wait_read<3>(); break;
+                }
+                if (nxt < n_tiles)
+                    for (int off = b * BOX_ROWS * 32; off < (b + 1) * BOX_ROWS * 32; off += CH)
+                        tma_load_1d(k3_smem + off, src + off, CH, bar);
+            }
+        }
     }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------- host ----
@@ -287,20 +355,27 @@ static kopek_status k3_get_plan(uint64_t n, int device, K3Plan *out) {
     return KOPEK_OK;
 }
 
-template <int N1> static cudaError_t launch_pass1(int grid, const CUtensorMap &a, const CUtensorMap &b, K3Tables tb,
-                                                  cudaStream_t st) {
+// persistent grid: as many CTAs as can be resident (occupancy x SMs), at most one per tile
+template <class K> static int k3_grid(K kern, int threads, int smem, int tiles, int sms) {
+    int nb = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem) != cudaSuccess || nb < 1) nb = 1;
+    long long g = (long long)nb * sms;
+    return (int)(g < tiles ? g : tiles);
+}
+template <int N1> static cudaError_t launch_pass1(int tiles, int sms, const CUtensorMap &a, const CUtensorMap &b,
+                                                  K3Tables tb, cudaStream_t st) {
     const int smem = N1 * 32 + 16;
     cudaError_t e = cudaFuncSetAttribute(k3_pass1<N1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    k3_pass1<N1><<<grid, N1 / 4, smem, st>>>(a, b, tb);
+    k3_pass1<N1><<<k3_grid(k3_pass1<N1>, N1 / 4, smem, tiles, sms), N1 / 4, smem, st>>>(a, b, tb, tiles);
     return cudaGetLastError();
 }
-template <int N2> static cudaError_t launch_pass2(int grid, const float2 *mid, const CUtensorMap &o, K3Tables tb,
-                                                  cudaStream_t st) {
+template <int N2> static cudaError_t launch_pass2(int tiles, int sms, const float2 *mid, const CUtensorMap &o,
+                                                  K3Tables tb, cudaStream_t st) {
     const int smem = N2 * 32 + 16;
     cudaError_t e = cudaFuncSetAttribute(k3_pass2<N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    k3_pass2<N2><<<grid, N2 / 4, smem, st>>>(mid, o, tb);
+    k3_pass2<N2><<<k3_grid(k3_pass2<N2>, N2 / 4, smem, tiles, sms), N2 / 4, smem, st>>>(mid, o, tb, tiles);
     return cudaGetLastError();
 }
 
@@ -332,21 +407,23 @@ extern "C" kopek_status kopek_fft_large_c2c_f32(const float *d_in, float *d_out,
         return fail(KOPEK_ERR_CUDA, "cuTensorMapEncodeTiled failed (driver entry point missing or bad geometry)");
     K3Tables tb{p.tw1, p.tw2, p.hi, p.lo};
     cudaStream_t stream = (cudaStream_t)cuda_stream;
+    int sms = 0;
+    KOPEK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     cudaError_t e = cudaErrorInvalidValue;
     switch (p.n1) {
-        case 256: e = launch_pass1<256>(p.n2 / 4, in_map, mid_map, tb, stream); break;
-        case 512: e = launch_pass1<512>(p.n2 / 4, in_map, mid_map, tb, stream); break;
-        case 1024: e = launch_pass1<1024>(p.n2 / 4, in_map, mid_map, tb, stream); break;
-        case 2048: e = launch_pass1<2048>(p.n2 / 4, in_map, mid_map, tb, stream); break;
-        case 4096: e = launch_pass1<4096>(p.n2 / 4, in_map, mid_map, tb, stream); break;
+        case 256: e = launch_pass1<256>(p.n2 / 4, sms, in_map, mid_map, tb, stream); break;
+        case 512: e = launch_pass1<512>(p.n2 / 4, sms, in_map, mid_map, tb, stream); break;
+        case 1024: e = launch_pass1<1024>(p.n2 / 4, sms, in_map, mid_map, tb, stream); break;
+        case 2048: e = launch_pass1<2048>(p.n2 / 4, sms, in_map, mid_map, tb, stream); break;
+        case 4096: e = launch_pass1<4096>(p.n2 / 4, sms, in_map, mid_map, tb, stream); break;
     }
     if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "four-step pass 1 (N1=%d): %s", p.n1, cudaGetErrorString(e));
     switch (p.n2) {
-        case 256: e = launch_pass2<256>(p.n1 / 4, p.mid, out_map, tb, stream); break;
-        case 512: e = launch_pass2<512>(p.n1 / 4, p.mid, out_map, tb, stream); break;
-        case 1024: e = launch_pass2<1024>(p.n1 / 4, p.mid, out_map, tb, stream); break;
-        case 2048: e = launch_pass2<2048>(p.n1 / 4, p.mid, out_map, tb, stream); break;
-        case 4096: e = launch_pass2<4096>(p.n1 / 4, p.mid, out_map, tb, stream); break;
+        case 256: e = launch_pass2<256>(p.n1 / 4, sms, p.mid, out_map, tb, stream); break;
+        case 512: e = launch_pass2<512>(p.n1 / 4, sms, p.mid, out_map, tb, stream); break;
+        case 1024: e = launch_pass2<1024>(p.n1 / 4, sms, p.mid, out_map, tb, stream); break;
+        case 2048: e = launch_pass2<2048>(p.n1 / 4, sms, p.mid, out_map, tb, stream); break;
+        case 4096: e = launch_pass2<4096>(p.n1 / 4, sms, p.mid, out_map, tb, stream); break;
         default: e = cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "four-step pass 2 (N2=%d): %s", p.n2, cudaGetErrorString(e));
