@@ -57,7 +57,7 @@ __device__ __forceinline__ void k3_stage(float2 *buf, const float2 *tw, int tid,
             if constexpr (TILE_MAJOR_IN) pos = ((q >> 2) << 4) + (c << 2) + (q & 3);   // [q/4][c][q%4]
             else pos = (READ_LINEAR ? q : k3_swz(q)) * 4 + c;
             float2 v = buf[pos];
-            if (NS > 1 && t > 0) v = cmul(v, __ldg(tw + (t - 1) * NS + kk));   // stage table, t-major
+            if (NS > 1 && t > 0) v = cmul(v, tw[(t - 1) * NS + kk]);           // stage table (shared), t-major
             d[i * RAD + t] = v;
         }
     }
@@ -69,15 +69,25 @@ __device__ __forceinline__ void k3_stage(float2 *buf, const float2 *tw, int tid,
         int j = tid + T * i;
         int kk = j & (NS - 1);
         int base = (j - kk) * RAD + kk;
+        if constexpr (XTW) {
+            // outputs q = base + k NS: W_n^{n2 q} = W_n^{n2 base} (W_n^{n2 NS})^k -- two table lookups per
+            // butterfly, the powers by squaring/multiplying (depth <= 4, error ~4 ulp)
+            const uint32_t m0 = n2 * (uint32_t)base, ms = n2 * (uint32_t)NS;
+            const float2 b0 = cmul(__ldg(tw_hi + (m0 >> 12)), __ldg(tw_lo + (m0 & 4095u)));
+            const float2 st = cmul(__ldg(tw_hi + (ms >> 12)), __ldg(tw_lo + (ms & 4095u)));
+            float2 pw[RAD];
+            pw[0] = make_float2(1.0f, 0.0f);
+            pw[1] = st;
+#pragma unroll
+            for (int k = 2; k < RAD; ++k) pw[k] = (k & 1) ? cmul(pw[k - 1], st) : cmul(pw[k / 2], pw[k / 2]);
+            d[i * RAD] = cmul(d[i * RAD], b0);
+#pragma unroll
+            for (int k = 1; k < RAD; ++k) d[i * RAD + k] = cmul(d[i * RAD + k], cmul(b0, pw[k]));
+        }
 #pragma unroll
         for (int k = 0; k < RAD; ++k) {
             int q = base + k * NS;
-            float2 v = d[i * RAD + k];
-            if constexpr (XTW) {
-                uint32_t m = n2 * (uint32_t)q;
-                v = cmul(v, cmul(__ldg(tw_hi + (m >> 12)), __ldg(tw_lo + (m & 4095u))));
-            }
-            buf[(WRITE_LINEAR ? q : k3_swz(q)) * 4 + c] = v;
+            buf[(WRITE_LINEAR ? q : k3_swz(q)) * 4 + c] = d[i * RAD + k];
         }
     }
     __syncthreads();
@@ -137,7 +147,9 @@ k3_pass1(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUt
          int n_tiles) {
     extern __shared__ __align__(128) unsigned char k3_smem[];
     float2 *buf = reinterpret_cast<float2 *>(k3_smem);                 // N1 x 4 complex, dense
-    uint64_t *bar = reinterpret_cast<uint64_t *>(k3_smem + (size_t)N1 * 32);
+    float2 *s_tw = reinterpret_cast<float2 *>(k3_smem + (size_t)N1 * 32);   // stage twiddles, N1 entries
+    uint64_t *bar = reinterpret_cast<uint64_t *>(k3_smem + (size_t)N1 * 40);
+    for (int i = threadIdx.x; i < N1; i += N1 / 4) s_tw[i] = tb.tw_sub1[i];
     constexpr int NBOX = N1 >= 1024 ? N1 / 1024 : 1;                   // load/store granule: 1024 rows = 32 KB
     constexpr int BOX_ROWS = N1 / NBOX;
     if (threadIdx.x == 0) {
@@ -156,7 +168,7 @@ k3_pass1(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUt
         mbar_wait(bar, phase);
         phase ^= 1;
         // sub-transform + inter-step twiddle W_n^{n2 k1}, n2 = 4s + c (fused into the last stage's write)
-        k3_fft_tile<N1, false, true>(buf, tb.tw_sub1, tid, c, 4u * s + c, tb.tw_hi, tb.tw_lo);
+        k3_fft_tile<N1, false, true>(buf, s_tw, tid, c, 4u * s + c, tb.tw_hi, tb.tw_lo);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic writes -> TMA store reads
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -193,7 +205,9 @@ __global__ void __launch_bounds__(N2 / 4, 1)
 k3_pass2(const float2 *__restrict__ mid, const __grid_constant__ CUtensorMap out_map, K3Tables tb, int n_tiles) {
     extern __shared__ __align__(128) unsigned char k3_smem[];
     float2 *buf = reinterpret_cast<float2 *>(k3_smem);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(k3_smem + (size_t)N2 * 32);
+    float2 *s_tw = reinterpret_cast<float2 *>(k3_smem + (size_t)N2 * 32);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(k3_smem + (size_t)N2 * 40);
+    for (int i = threadIdx.x; i < N2; i += N2 / 4) s_tw[i] = tb.tw_sub2[i];
     constexpr int NBOX = N2 >= 1024 ? N2 / 1024 : 1;
     constexpr int BOX_ROWS = N2 / NBOX;
     constexpr int CH = BOX_ROWS * 32 < 16384 ? BOX_ROWS * 32 : 16384;    // 1-D bulk copy granule
@@ -213,7 +227,7 @@ k3_pass2(const float2 *__restrict__ mid, const __grid_constant__ CUtensorMap out
     for (int u = blockIdx.x; u < n_tiles; u += gridDim.x) {
         mbar_wait(bar, phase);
         phase ^= 1;
-        k3_fft_tile<N2, true, false>(buf, tb.tw_sub2, tid, c);
+        k3_fft_tile<N2, true, false>(buf, s_tw, tid, c);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -364,7 +378,7 @@ template <class K> static int k3_grid(K kern, int threads, int smem, int tiles, 
 }
 template <int N1> static cudaError_t launch_pass1(int tiles, int sms, const CUtensorMap &a, const CUtensorMap &b,
                                                   K3Tables tb, cudaStream_t st) {
-    const int smem = N1 * 32 + 16;
+    const int smem = N1 * 40 + 16;
     cudaError_t e = cudaFuncSetAttribute(k3_pass1<N1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     k3_pass1<N1><<<k3_grid(k3_pass1<N1>, N1 / 4, smem, tiles, sms), N1 / 4, smem, st>>>(a, b, tb, tiles);
@@ -372,7 +386,7 @@ template <int N1> static cudaError_t launch_pass1(int tiles, int sms, const CUte
 }
 template <int N2> static cudaError_t launch_pass2(int tiles, int sms, const float2 *mid, const CUtensorMap &o,
                                                   K3Tables tb, cudaStream_t st) {
-    const int smem = N2 * 32 + 16;
+    const int smem = N2 * 40 + 16;
     cudaError_t e = cudaFuncSetAttribute(k3_pass2<N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     k3_pass2<N2><<<k3_grid(k3_pass2<N2>, N2 / 4, smem, tiles, sms), N2 / 4, smem, st>>>(mid, o, tb, tiles);
