@@ -94,11 +94,13 @@ template <> struct Dft<16> {
 
 // ---- per-size configuration -------------------------------------------------
 template <int N_> struct K1Cfg;
-template <> struct K1Cfg<256>  { static constexpr int S = 2, R0 = 8,  R1 = 16, R2 = 1;  static constexpr int SWZ_SHIFT = 4; };
-template <> struct K1Cfg<512>  { static constexpr int S = 2, R0 = 16, R1 = 16, R2 = 1;  static constexpr int SWZ_SHIFT = 4; };
-template <> struct K1Cfg<1024> { static constexpr int S = 3, R0 = 8,  R1 = 8,  R2 = 8;  static constexpr int SWZ_SHIFT = 3; };
-template <> struct K1Cfg<2048> { static constexpr int S = 3, R0 = 4,  R1 = 16, R2 = 16; static constexpr int SWZ_SHIFT = 4; };
-template <> struct K1Cfg<4096> { static constexpr int S = 3, R0 = 8,  R1 = 16, R2 = 16; static constexpr int SWZ_SHIFT = 4; };
+// radices, XOR swizzle q ^ ((q >> SWZ_SHIFT) & SWZ_MASK) and per-frame padding (complex slots) of the exchange
+// buffer -- chosen with tools/bank_check.py (wavefronts within 1.08-1.13x of the conflict-free minimum)
+template <> struct K1Cfg<256>  { static constexpr int S = 2, R0 = 8,  R1 = 16, R2 = 1;  static constexpr int SWZ_SHIFT = 3, SWZ_MASK = 7,  PAD = 8; };
+template <> struct K1Cfg<512>  { static constexpr int S = 2, R0 = 16, R1 = 16, R2 = 1;  static constexpr int SWZ_SHIFT = 4, SWZ_MASK = 15, PAD = 0; };
+template <> struct K1Cfg<1024> { static constexpr int S = 3, R0 = 8,  R1 = 8,  R2 = 8;  static constexpr int SWZ_SHIFT = 3, SWZ_MASK = 15, PAD = 0; };
+template <> struct K1Cfg<2048> { static constexpr int S = 3, R0 = 4,  R1 = 16, R2 = 16; static constexpr int SWZ_SHIFT = 4, SWZ_MASK = 15, PAD = 0; };
+template <> struct K1Cfg<4096> { static constexpr int S = 3, R0 = 8,  R1 = 16, R2 = 16; static constexpr int SWZ_SHIFT = 4, SWZ_MASK = 15, PAD = 0; };
 
 // Host: fill the M-entry stage-twiddle table of frame size N_ (stage 1 block, then stage 2 block).
 template <int N_> inline void k1_build_stage_twiddles(float2 *out) {
@@ -126,8 +128,9 @@ template <int N_> struct K1Geom {
     static constexpr int FPB = BLOCK / T;                  // frames per CTA per iteration
     static constexpr int PW = M / 2 + 2;                   // post twiddles (padded to even)
     // shared memory (bytes): stage twiddles, post twiddles, window, exchange buffers
-    static constexpr size_t SMEM = sizeof(float2) * (M + PW + FPB * M) + sizeof(float) * N;
-    __host__ __device__ static constexpr int swz(int q) { return q ^ ((q >> C::SWZ_SHIFT) & 15); }
+    static constexpr int FSTRIDE = M + C::PAD;             // exchange-buffer slots per frame
+    static constexpr size_t SMEM = sizeof(float2) * (M + PW + FPB * FSTRIDE) + sizeof(float) * N;
+    __host__ __device__ static constexpr int swz(int q) { return q ^ ((q >> C::SWZ_SHIFT) & C::SWZ_MASK); }
 };
 
 struct K1Params {
@@ -216,7 +219,7 @@ k1_stft_kernel(const K1Params p) {
     float2 *s_tw = reinterpret_cast<float2 *>(smem_raw);
     float2 *s_pw = s_tw + M;
     float2 *s_ex = s_pw + G::PW;
-    float *s_win = reinterpret_cast<float *>(s_ex + G::FPB * M);
+    float *s_win = reinterpret_cast<float *>(s_ex + G::FPB * G::FSTRIDE);
 
     for (int i = threadIdx.x; i < M; i += G::BLOCK) s_tw[i] = p.tw[i];
     for (int i = threadIdx.x; i <= M / 2; i += G::BLOCK) s_pw[i] = p.pw[i];
@@ -226,7 +229,7 @@ k1_stft_kernel(const K1Params p) {
 
     const int tid = threadIdx.x % T;
     const int fslot = threadIdx.x / T;
-    float2 *buf = s_ex + fslot * M;
+    float2 *buf = s_ex + fslot * G::FSTRIDE;
     const uint64_t n_groups = (p.n_frames + G::FPB - 1) / G::FPB;
 
     for (uint64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
