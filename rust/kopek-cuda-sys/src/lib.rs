@@ -21,11 +21,18 @@ pub const KOPEK_OUT_COMPLEX: u32 = 0;
 pub const KOPEK_OUT_MAG: u32 = 1;
 pub const KOPEK_OUT_POWER: u32 = 2;
 pub const KOPEK_OUT_DB: u32 = 3;
+pub const KOPEK_OUT_BANDS_LOG: u32 = 4;
+pub const KOPEK_OUT_BANDS_LOW: u32 = 5;
+pub const KOPEK_BAND_ROW: usize = 10;
 pub const KOPEK_BINS_HALF: u32 = 0;
 pub const KOPEK_BINS_FULL: u32 = 1;
 
 #[repr(C)]
 pub struct kopek_plan {
+    _private: [u8; 0],
+}
+#[repr(C)]
+pub struct kopek_stream {
     _private: [u8; 0],
 }
 
@@ -46,6 +53,7 @@ extern "C" {
     pub fn kopek_plan_create(plan: *mut *mut kopek_plan, n: u32, hop: u32, window: u32, output: u32, bins: u32,
                              out_pitch_elems: u64, device: c_int) -> kopek_status;
     pub fn kopek_plan_set_window(plan: *mut kopek_plan, window_host: *const f32) -> kopek_status;
+    pub fn kopek_plan_set_band_scale(plan: *mut kopek_plan, scale: f32) -> kopek_status;
     pub fn kopek_plan_destroy(plan: *mut kopek_plan) -> kopek_status;
     pub fn kopek_plan_frames(plan: *const kopek_plan, n_samples: u64) -> u64;
     pub fn kopek_plan_bins(plan: *const kopek_plan) -> u64;
@@ -56,6 +64,12 @@ extern "C" {
                            n_frames_out: *mut u64, cuda_stream: *mut c_void) -> kopek_status;
     pub fn kopek_stft_exec_host(plan: *mut kopek_plan, h_samples: *const f32, n_samples: u64, h_out: *mut c_void,
                                 n_frames_out: *mut u64) -> kopek_status;
+    pub fn kopek_stream_create(stream: *mut *mut kopek_stream, n: u32, window: u32, output: u32, input_scale: f32,
+                               device: c_int) -> kopek_status;
+    pub fn kopek_stream_push(stream: *mut kopek_stream, h_samples: *const f32, count: u32, h_out: *mut c_void)
+                             -> kopek_status;
+    pub fn kopek_stream_bins(stream: *const kopek_stream) -> u64;
+    pub fn kopek_stream_destroy(stream: *mut kopek_stream) -> kopek_status;
     pub fn kopek_host_alloc(ptr: *mut *mut c_void, bytes: usize) -> kopek_status;
     pub fn kopek_host_free(ptr: *mut c_void) -> kopek_status;
 

@@ -36,6 +36,13 @@ def test_python_binding_covers_header(built_lib):
     assert lib.kopek_version().decode().startswith("kopek_b200")
 
 
+def test_rust_sys_crate_declares_every_symbol():
+    """rust/kopek-cuda-sys cannot be compiled here (no rustc); keep it textually in step with the header."""
+    text = open(os.path.join(ROOT, "rust", "kopek-cuda-sys", "src", "lib.rs")).read()
+    declared = set(re.findall(r"pub fn (kopek_\w+)\s*\(", text))
+    assert declared == set(_declared_symbols())
+
+
 def test_library_has_sm100a_code_only(built_lib):
     out = subprocess.run(["cuobjdump", "-lelf", built_lib], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_(\d+a?)", out))
