@@ -1,0 +1,66 @@
+"""GPU: out-of-bounds canaries (compute-sanitizer is closed on this pool): every kernel writes into the middle of a
+sentinel-filled allocation and must leave the guard zones before and after its output untouched."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GUARD = 4096          # elements on each side
+SENT = -12345.0
+
+
+def _guarded(n_elems, dtype):
+    import torch
+    buf = torch.full((n_elems + 2 * GUARD,), SENT, device="cuda", dtype=dtype)
+    return buf, buf[GUARD:GUARD + n_elems]
+
+
+def _check(buf, n_elems):
+    import torch
+    torch.cuda.synchronize()
+    lo, hi = buf[:GUARD], buf[GUARD + n_elems:]
+    ref = torch.full_like(lo, SENT)
+    assert torch.equal(lo, ref) and torch.equal(hi, ref), "kernel wrote outside its output"
+    assert not bool((buf[GUARD:GUARD + n_elems] == SENT).any()), "kernel left output elements unwritten"
+
+
+@pytest.mark.parametrize("n,hop,window,output", [
+    (1024, 1024, 1, 1), (1024, 1024, 0, 3), (1024, 256, 1, 0), (1024, 1024, 0, 4), (1024, 1024, 1, 5),
+    (1024, 333, 1, 1), (256, 256, 0, 1), (512, 128, 1, 2), (2048, 512, 1, 3), (4096, 1024, 1, 1), (4096, 4096, 0, 0)])
+def test_stft_kernels_stay_in_bounds(built_lib, n, hop, window, output):
+    import torch
+    from kopek_b200 import StftPlan
+    frames = 1237                                     # not a multiple of frames-per-CTA or of the resident warps
+    ns = (frames - 1) * hop + n
+    xin, x = _guarded(ns, torch.float32)
+    x.copy_(torch.randn(ns, device="cuda") + 2.0)     # strictly non-zero spectra so "unwritten" is detectable
+    with StftPlan(n, hop, window, output) as plan:
+        ne = frames * plan.pitch
+        obuf, out = _guarded(ne, torch.complex64 if output == 0 else torch.float32)
+        assert plan.exec_ptr(x.data_ptr(), ns, out.data_ptr(), torch.cuda.current_stream().cuda_stream) == frames
+        _check(obuf, ne)
+    # the input guards are untouched as well (kernels only read, TMA prefetch must not run past the last frame)
+    torch.cuda.synchronize()
+    assert bool((xin[:GUARD] == SENT).all()) and bool((xin[GUARD + ns:] == SENT).all())
+
+
+@pytest.mark.parametrize("log_n", [16, 19, 22])
+def test_large_fft_stays_in_bounds(built_lib, log_n):
+    import torch
+    from kopek_b200 import fft
+    n = 1 << log_n
+    a = torch.randn(n, dtype=torch.complex64, device="cuda") + 1.0
+    obuf, out = _guarded(n, torch.complex64)
+    fft.fft_large_device(a.data_ptr(), out.data_ptr(), n, 0, torch.cuda.current_stream().cuda_stream)
+    _check(obuf, n)
+
+
+def test_drop_in_device_stays_in_bounds(built_lib):
+    import torch
+    from kopek_b200 import _lib
+    batch, n_in = 37, 1000
+    x = torch.randn((batch, n_in), dtype=torch.complex128, device="cuda") + 1.0
+    obuf, out = _guarded(batch * 1024, torch.complex128)
+    _lib.check(_lib.load().kopek_fft_c2c_f64_device(x.data_ptr(), n_in, batch, out.data_ptr(), 0,
+                                                    torch.cuda.current_stream().cuda_stream))
+    _check(obuf, batch * 1024)
