@@ -119,6 +119,18 @@ __device__ __forceinline__ int band_low_of(int k) {
     return (k >= 20 && k < 44) ? ((k - 20) * 11) >> 5 : -1;      // x*11>>5 == x/3 for 0 <= x < 24
 }
 
+// W1024^{8 f + 64 k0} (index 2 k0 + f): the compile-time part of the split twiddle -i W1024^{kbase + 8 f + 64 k0};
+// the lane part -i W1024^{kbase} is one register pair.  Saves the 16 wavefronts of a post-twiddle table per frame.
+__device__ __forceinline__ float2 mul_w1024_off(float2 a, int idx) {
+    constexpr float c[8] = {1.0f, 0.99879545620517240501f, 0.92387953251128673848f, 0.90398929312344333820f,
+                            0.70710678118654757274f, 0.67155895484701833009f, 0.38268343236508983729f,
+                            0.33688985339222005111f};
+    constexpr float s[8] = {0.0f, -0.04906767432741801493f, -0.38268343236508978178f, -0.42755509343028208491f,
+                            -0.70710678118654746172f, -0.74095112535495910588f, -0.92387953251128673848f,
+                            -0.94154406518302080631f};
+    return idx == 0 ? a : cmul_const(a, c[idx], s[idx]);
+}
+
 // TWREG: pass-A/B twiddles live in registers (loop invariant per lane) instead of shared memory;
 // WINREG: so does the lane's slice of the window.
 // TMA: the NEXT frame of the warp is fetched by one cp.async.bulk into the warp's landing buffer while
@@ -155,6 +167,7 @@ k1w_1024_kernel(const K1WParams p) {
     const float4 *pwt = s_pw + l;                            // + 32 k0
     const float4 *wt = s_win + l;                            // + 32 n2
     const int kbase = (l >> 2) + 16 * (l & 3);               // k = kbase + 8 f + 64 k0
+    const float2 pw_lane = make_float2(pwt[0].x, pwt[0].y);  // -i W1024^{kbase}
     float2 rp[8], rp1[8], rq[8], rq1[8];                     // TWREG: W256^{l k2}, W512^{(2l+1) k2}, W32^{b k1}, W64^{(2b+1) k1}
     float4 rw[8];                                            // WINREG: window slice
     if constexpr (TWREG) {
@@ -319,16 +332,14 @@ k1w_1024_kernel(const K1WParams p) {
         char *o_hi = reinterpret_cast<char *>(p.out) + (frame * p.pitch + (M - kbase)) * EB;
 #pragma unroll
         for (int k0 = 0; k0 < 4; ++k0) {
-            float4 w = pwt[32 * k0];
 #pragma unroll
             for (int f = 0; f < 2; ++f) {
                 const int koff = (8 * f + 64 * k0) * EB;
                 const float2 a = f ? d1[k0] : d0[k0];
                 const float2 b = f ? b1[k0] : b0[k0];
-                const float2 tw = f ? make_float2(w.z, w.w) : make_float2(w.x, w.y);
                 float2 S = make_float2(a.x + b.x, a.y - b.y);
                 float2 D = make_float2(a.x - b.x, a.y + b.y);
-                float2 Q = cmul(D, tw);
+                float2 Q = cmul(mul_w1024_off(D, 2 * k0 + f), pw_lane);
                 if constexpr (BANDS) {
                     // |X[k]| joins its band; |X[M-k]| (bins 256..511) is band 7 of the log set
                     const float2 X1 = S + Q;

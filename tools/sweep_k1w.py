@@ -22,7 +22,7 @@ for window, output in ((1, 1), (0, 1)):
         for _ in range(3):
             plan.exec_ptr(x.data_ptr(), x.numel(), out.data_ptr(), st)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        iters = 20
+        iters = int(os.environ.get("SWEEP_ITERS", "20"))
         e0.record()
         for _ in range(iters):
             plan.exec_ptr(x.data_ptr(), x.numel(), out.data_ptr(), st)
