@@ -5,13 +5,13 @@
 // transform its two 256 MiB ping-pong buffers are walked with strides up to 2^23 elements.  Here:
 //
 //   n = n1 N2 + n2,  k = k1 + N1 k2
-//   pass 1 (one CTA per tile of 4 columns n2):  A[k1][n2] = W_n^{n2 k1} * sum_n1 x[n1 N2 + n2] W_N1^{n1 k1}
+//   pass 1 (one CTA per tile of 2 columns n2):  A[k1][n2] = W_n^{n2 k1} * sum_n1 x[n1 N2 + n2] W_N1^{n1 k1}
 //   pass 2 (one CTA per tile of 4 rows k1):     X[k1 + N1 k2] = sum_n2 A[k1][n2] W_N2^{n2 k2}
 //
 // Two HBM passes (the minimum for a transform that does not fit on chip).  Every global access is a
-// TMA tile: pass 1 loads a [N1 x 4] column tile with 2-D boxes (32-byte rows) and stores its result
-// TILE-MAJOR -- mid[k1/4][n2][k1%4], 128-byte segments -- so that pass 2 loads ONE contiguous block per
-// CTA (1-D bulk copies) and stores [N2 x 4] tiles of the natural-order output.  Both transposes and the
+// TMA tile: pass 1 loads a [N1 x 2] column tile with 2-D boxes (16-byte rows, two CTAs per SM) and stores its
+// result TILE-MAJOR -- mid[k1/4][n2/2][k1%4][n2%2], 64-byte segments -- so that pass 2 loads ONE contiguous
+// block per CTA (1-D bulk copies) and stores [N2 x 4] tiles of the natural-order output.  Both transposes and the
 // inter-step twiddle are fused into the passes; there is no standalone transpose kernel.
 // The sub-transforms are Stockham radix-4/8/16 in shared memory with the four tile columns interleaved
 // (column index fastest across lanes), which keeps every shared access contiguous.
@@ -41,7 +41,8 @@ __host__ __device__ constexpr int k3_swz(int q) { return q ^ ((q >> 4) & 15); }
 // FIRST_MAP remaps the logical index of the very first read (pass 2: tile-major block order).
 // XTW (last stage of pass 1 only): the inter-step twiddle W_n^{n2 q} is applied to output q in registers just
 // before the final write (two-level table: W^m = W^{4096 (m >> 12)} W^{m & 4095}), saving a pass over the tile.
-template <int RAD, int NS, int M, int T, bool READ_LINEAR, bool WRITE_LINEAR, bool TILE_MAJOR_IN, bool XTW = false>
+template <int COLS, int RAD, int NS, int M, int T, bool READ_LINEAR, bool WRITE_LINEAR, bool TILE_MAJOR_IN,
+          bool XTW = false>
 __device__ __forceinline__ void k3_stage(float2 *buf, const float2 *tw, int tid, int c, uint32_t n2 = 0,
                                          const float2 *tw_hi = nullptr, const float2 *tw_lo = nullptr) {
     constexpr int NB = 16 / RAD;
@@ -54,8 +55,8 @@ __device__ __forceinline__ void k3_stage(float2 *buf, const float2 *tw, int tid,
         for (int t = 0; t < RAD; ++t) {
             int q = j + t * (M / RAD);
             int pos;
-            if constexpr (TILE_MAJOR_IN) pos = ((q >> 2) << 4) + (c << 2) + (q & 3);   // [q/4][c][q%4]
-            else pos = (READ_LINEAR ? q : k3_swz(q)) * 4 + c;
+            if constexpr (TILE_MAJOR_IN) pos = (q >> 1) * (2 * COLS) + (c << 1) + (q & 1);   // mid tile: [q/2][c][q%2]
+            else pos = (READ_LINEAR ? q : k3_swz(q)) * COLS + c;
             float2 v = buf[pos];
             if (NS > 1 && t > 0) v = cmul(v, tw[(t - 1) * NS + kk]);           // stage table (shared), t-major
             d[i * RAD + t] = v;
@@ -87,26 +88,26 @@ __device__ __forceinline__ void k3_stage(float2 *buf, const float2 *tw, int tid,
 #pragma unroll
         for (int k = 0; k < RAD; ++k) {
             int q = base + k * NS;
-            buf[(WRITE_LINEAR ? q : k3_swz(q)) * 4 + c] = d[i * RAD + k];
+            buf[(WRITE_LINEAR ? q : k3_swz(q)) * COLS + c] = d[i * RAD + k];
         }
     }
     __syncthreads();
 }
 
-// M-point FFT of the 4 interleaved columns in `buf`; result dense: buf[k * 4 + c].
-template <int M, bool TILE_MAJOR_IN, bool XTW>
+// M-point FFT of the COLS interleaved columns in `buf`; result dense: buf[k * COLS + c].
+template <int COLS, int M, bool TILE_MAJOR_IN, bool XTW>
 __device__ __forceinline__ void k3_fft_tile(float2 *buf, const float2 *tw, int tid, int c, uint32_t n2 = 0,
                                             const float2 *tw_hi = nullptr, const float2 *tw_lo = nullptr) {
     using C = K3Cfg<M>;
     constexpr int T = M / 16;
     if constexpr (C::R2 > 1) {
-        k3_stage<C::R0, 1, M, T, true, false, TILE_MAJOR_IN>(buf, tw, tid, c);
-        k3_stage<C::R1, C::R0, M, T, false, false, false>(buf, tw, tid, c);
-        k3_stage<C::R2, C::R0 * C::R1, M, T, false, true, false, XTW>(buf, tw + (C::R1 - 1) * C::R0, tid, c, n2, tw_hi,
-                                                                       tw_lo);
+        k3_stage<COLS, C::R0, 1, M, T, true, false, TILE_MAJOR_IN>(buf, tw, tid, c);
+        k3_stage<COLS, C::R1, C::R0, M, T, false, false, false>(buf, tw, tid, c);
+        k3_stage<COLS, C::R2, C::R0 * C::R1, M, T, false, true, false, XTW>(buf, tw + (C::R1 - 1) * C::R0, tid, c, n2,
+                                                                             tw_hi, tw_lo);
     } else {
-        k3_stage<C::R0, 1, M, T, true, false, TILE_MAJOR_IN>(buf, tw, tid, c);
-        k3_stage<C::R1, C::R0, M, T, false, true, false, XTW>(buf, tw, tid, c, n2, tw_hi, tw_lo);
+        k3_stage<COLS, C::R0, 1, M, T, true, false, TILE_MAJOR_IN>(buf, tw, tid, c);
+        k3_stage<COLS, C::R1, C::R0, M, T, false, true, false, XTW>(buf, tw, tid, c, n2, tw_hi, tw_lo);
     }
 }
 
@@ -140,47 +141,50 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 // box b out of shared memory (wait_group.read) the same box of the NEXT tile is loaded into it, so the
 // store of tile i and the load of tile i+1 overlap (only the FFT itself is not overlapped with memory).
 
-// ---- pass 1: column tiles s (columns 4s..4s+3), all n1
+// ---- pass 1: column tiles s (columns 2s, 2s+1), all n1.  Two-column tiles (N1 x 16 B = 64 KB at N1 = 4096)
+// let TWO CTAs share an SM, so one transforms while the other waits on shared memory or on its TMA
+// traffic (a single 128 KB tile per SM ran its 32 warps in lockstep between __syncthreads).  The two halves
+// of every 32-byte DRAM sector are fetched by neighbouring CTAs at about the same time and merge in L2.
 template <int N1>
-__global__ void __launch_bounds__(N1 / 4, 1)
+__global__ void __launch_bounds__(N1 / 8, 2)
 k3_pass1(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap mid_map, K3Tables tb,
          int n_tiles) {
     extern __shared__ __align__(128) unsigned char k3_smem[];
-    float2 *buf = reinterpret_cast<float2 *>(k3_smem);                 // N1 x 4 complex, dense
-    float2 *s_tw = reinterpret_cast<float2 *>(k3_smem + (size_t)N1 * 32);   // stage twiddles, N1 entries
-    uint64_t *bar = reinterpret_cast<uint64_t *>(k3_smem + (size_t)N1 * 40);
-    for (int i = threadIdx.x; i < N1; i += N1 / 4) s_tw[i] = tb.tw_sub1[i];
-    constexpr int NBOX = N1 >= 1024 ? N1 / 1024 : 1;                   // load/store granule: 1024 rows = 32 KB
+    float2 *buf = reinterpret_cast<float2 *>(k3_smem);                 // N1 x 2 complex, dense
+    float2 *s_tw = reinterpret_cast<float2 *>(k3_smem + (size_t)N1 * 16);   // stage twiddles, N1 entries
+    uint64_t *bar = reinterpret_cast<uint64_t *>(k3_smem + (size_t)N1 * 24);
+    for (int i = threadIdx.x; i < N1; i += N1 / 8) s_tw[i] = tb.tw_sub1[i];
+    constexpr int NBOX = N1 >= 1024 ? N1 / 1024 : 1;                   // load/store granule: 1024 rows = 16 KB
     constexpr int BOX_ROWS = N1 / NBOX;
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if ((int)blockIdx.x < n_tiles) {
-            mbar_expect_tx(bar, N1 * 32);
-            for (int r0 = 0; r0 < N1; r0 += 256) tma_load_2d(buf + r0 * 4, &in_map, 8 * blockIdx.x, r0, bar);
+            mbar_expect_tx(bar, N1 * 16);
+            for (int r0 = 0; r0 < N1; r0 += 256) tma_load_2d(buf + r0 * 2, &in_map, 4 * blockIdx.x, r0, bar);
         }
     }
     __syncthreads();
-    const int c = threadIdx.x & 3, tid = threadIdx.x >> 2;
+    const int c = threadIdx.x & 1, tid = threadIdx.x >> 1;
     uint32_t phase = 0;
     for (int s = blockIdx.x; s < n_tiles; s += gridDim.x) {
         mbar_wait(bar, phase);
         phase ^= 1;
-        // sub-transform + inter-step twiddle W_n^{n2 k1}, n2 = 4s + c (fused into the last stage's write)
-        k3_fft_tile<N1, false, true>(buf, s_tw, tid, c, 4u * s + c, tb.tw_hi, tb.tw_lo);
+        // sub-transform + inter-step twiddle W_n^{n2 k1}, n2 = 2s + c (fused into the last stage's write)
+        k3_fft_tile<2, N1, false, true>(buf, s_tw, tid, c, 2u * s + c, tb.tw_hi, tb.tw_lo);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic writes -> TMA store reads
         __syncthreads();
         if (threadIdx.x == 0) {
-            // buf is [k1][c] dense = rows u = k1/4 of 16 complex (32 floats): the 128-byte segments of mid
+            // buf is [k1][c] dense = rows u = k1/4 of 8 complex (16 floats): the 64-byte segments of mid
 #pragma unroll
             for (int b = 0; b < NBOX; ++b) {
                 for (int u0 = b * (BOX_ROWS / 4); u0 < (b + 1) * (BOX_ROWS / 4); u0 += 256)
-                    tma_store_2d(&mid_map, 32 * s, u0, buf + u0 * 16);
+                    tma_store_2d(&mid_map, 16 * s, u0, buf + u0 * 8);
                 tma_store_commit();
             }
             const int nxt = s + gridDim.x;
-            if (nxt < n_tiles) mbar_expect_tx(bar, N1 * 32);
+            if (nxt < n_tiles) mbar_expect_tx(bar, N1 * 16);
 #pragma unroll
             for (int b = 0; b < NBOX; ++b) {
                 // box b has left shared memory once at most NBOX-1-b younger groups are still reading
@@ -192,7 +196,7 @@ k3_pass1(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUt
                 }
                 if (nxt < n_tiles)
                     for (int r0 = b * BOX_ROWS; r0 < (b + 1) * BOX_ROWS; r0 += 256)
-                        tma_load_2d(buf + r0 * 4, &in_map, 8 * nxt, r0, bar);
+                        tma_load_2d(buf + r0 * 2, &in_map, 4 * nxt, r0, bar);
             }
         }
     }
@@ -227,7 +231,7 @@ k3_pass2(const float2 *__restrict__ mid, const __grid_constant__ CUtensorMap out
     for (int u = blockIdx.x; u < n_tiles; u += gridDim.x) {
         mbar_wait(bar, phase);
         phase ^= 1;
-        k3_fft_tile<N2, true, false>(buf, s_tw, tid, c);
+        k3_fft_tile<4, N2, true, false>(buf, s_tw, tid, c);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -378,10 +382,10 @@ template <class K> static int k3_grid(K kern, int threads, int smem, int tiles, 
 }
 template <int N1> static cudaError_t launch_pass1(int tiles, int sms, const CUtensorMap &a, const CUtensorMap &b,
                                                   K3Tables tb, cudaStream_t st) {
-    const int smem = N1 * 40 + 16;
+    const int smem = N1 * 24 + 16;
     cudaError_t e = cudaFuncSetAttribute(k3_pass1<N1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    k3_pass1<N1><<<k3_grid(k3_pass1<N1>, N1 / 4, smem, tiles, sms), N1 / 4, smem, st>>>(a, b, tb, tiles);
+    k3_pass1<N1><<<k3_grid(k3_pass1<N1>, N1 / 8, smem, tiles, sms), N1 / 8, smem, st>>>(a, b, tb, tiles);
     return cudaGetLastError();
 }
 template <int N2> static cudaError_t launch_pass2(int tiles, int sms, const float2 *mid, const CUtensorMap &o,
@@ -411,12 +415,13 @@ extern "C" kopek_status kopek_fft_large_c2c_f32(const float *d_in, float *d_out,
     kopek_status st = k3_get_plan(n, device, &p);
     if (st != KOPEK_OK) return st;
     CUtensorMap in_map, mid_map, out_map;
-    // in:  [N1 rows][N2 complex]          box 4 complex x 256 rows
-    // mid: [N1/4 rows][N2*4 complex]      box 16 complex x 256 rows (tile-major, 128-byte segments)
-    // out: [N2 rows][N1 complex]          box 4 complex x 256 rows
+    // in:  [N1 rows][N2 complex]          box 2 complex x 256 rows   (pass 1: two-column tiles)
+    // mid: [N1/4 rows][N2*4 complex]      box 8 complex x 256 rows   (tile-major [k1/4][n2/2][k1%4][n2%2], 64-byte segments)
+    // out: [N2 rows][N1 complex]          box 4 complex x 256 rows   (pass 2: four-row tiles; two-row tiles with
+    //                                      16-byte stores were measured slower: 0.184 ms vs 0.162 ms at 2^24)
     const uint32_t r1 = p.n1 < 256 ? p.n1 : 256, rm = p.n1 / 4 < 256 ? p.n1 / 4 : 256, r2 = p.n2 < 256 ? p.n2 : 256;
-    if (!make_map(&in_map, d_in, 2ull * p.n2, p.n1, 8, r1) ||
-        !make_map(&mid_map, p.mid, 8ull * p.n2, p.n1 / 4, 32, rm) ||
+    if (!make_map(&in_map, d_in, 2ull * p.n2, p.n1, 4, r1) ||
+        !make_map(&mid_map, p.mid, 8ull * p.n2, p.n1 / 4, 16, rm) ||
         !make_map(&out_map, d_out, 2ull * p.n1, p.n2, 8, r2))
         return fail(KOPEK_ERR_CUDA, "cuTensorMapEncodeTiled failed (driver entry point missing or bad geometry)");
     K3Tables tb{p.tw1, p.tw2, p.hi, p.lo};
@@ -425,11 +430,11 @@ extern "C" kopek_status kopek_fft_large_c2c_f32(const float *d_in, float *d_out,
     KOPEK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     cudaError_t e = cudaErrorInvalidValue;
     switch (p.n1) {
-        case 256: e = launch_pass1<256>(p.n2 / 4, sms, in_map, mid_map, tb, stream); break;
-        case 512: e = launch_pass1<512>(p.n2 / 4, sms, in_map, mid_map, tb, stream); break;
-        case 1024: e = launch_pass1<1024>(p.n2 / 4, sms, in_map, mid_map, tb, stream); break;
-        case 2048: e = launch_pass1<2048>(p.n2 / 4, sms, in_map, mid_map, tb, stream); break;
-        case 4096: e = launch_pass1<4096>(p.n2 / 4, sms, in_map, mid_map, tb, stream); break;
+        case 256: e = launch_pass1<256>(p.n2 / 2, sms, in_map, mid_map, tb, stream); break;
+        case 512: e = launch_pass1<512>(p.n2 / 2, sms, in_map, mid_map, tb, stream); break;
+        case 1024: e = launch_pass1<1024>(p.n2 / 2, sms, in_map, mid_map, tb, stream); break;
+        case 2048: e = launch_pass1<2048>(p.n2 / 2, sms, in_map, mid_map, tb, stream); break;
+        case 4096: e = launch_pass1<4096>(p.n2 / 2, sms, in_map, mid_map, tb, stream); break;
     }
     if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "four-step pass 1 (N1=%d): %s", p.n1, cudaGetErrorString(e));
     switch (p.n2) {
