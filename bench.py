@@ -123,7 +123,7 @@ def cpu_port_rate(frames: int, threads: int):
     return frames * N_FFT / dt, dt
 
 
-def cpu_baseline(target_s: float = 12.0):
+def cpu_baseline(target_s: float = 18.0):
     import oracle
     oracle.build()
     cores = oracle.max_threads()

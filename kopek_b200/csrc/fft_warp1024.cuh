@@ -131,13 +131,15 @@ __device__ __forceinline__ float2 mul_w1024_off(float2 a, int idx) {
     return idx == 0 ? a : cmul_const(a, c[idx], s[idx]);
 }
 
-// TWREG: pass-A/B twiddles live in registers (loop invariant per lane) instead of shared memory;
+// TWREG: 0 = pass-A/B twiddles from shared-memory tables; 2 = all four sets live in registers (loop invariant per
+//        lane, 56 registers); 1 = only the even-element sets do (28 registers), the odd element's twiddle is the
+//        even one times a compile-time rotation (W512^{k2}, W64^{k1}: +56 FP instructions per frame);
 // WINREG: so does the lane's slice of the window.
 // TMA: the NEXT frame of the warp is fetched by one cp.async.bulk into the warp's landing buffer while
 //      the current one is transformed (the buffer is free as soon as pass A has read it).
 // LOAD: 0 = plain LDG.128 at the top of the frame, 1 = TMA prefetch (above), 2 = LDG.128 of the next frame
 //       into registers at the top of the current one (no shared-memory landing traffic, 32 more registers).
-template <int OUT, bool WIN, int WARPS, int MINB, bool TWREG, bool WINREG, int LOAD>
+template <int OUT, bool WIN, int WARPS, int MINB, int TWREG, bool WINREG, int LOAD>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 k1w_1024_kernel(const K1WParams p) {
     constexpr int M = 512;
@@ -255,7 +257,8 @@ k1w_1024_kernel(const K1WParams p) {
             float2 a, b;
             if constexpr (TWREG) {
                 a = cmul(d0[k2], rp[k2]);
-                b = cmul(d1[k2], rp1[k2]);
+                if constexpr (TWREG == 2) b = cmul(d1[k2], rp1[k2]);
+                else b = cmul(mul_w512(d1[k2], k2), rp[k2]);
             } else {
                 float4 t = tpp[32 * (k2 - 1)];
                 a = cmul(d0[k2], make_float2(t.x, t.y));
@@ -279,7 +282,8 @@ k1w_1024_kernel(const K1WParams p) {
             float2 a, b;
             if constexpr (TWREG) {
                 a = cmul(d0[k1], rq[k1]);
-                b = cmul(d1[k1], rq1[k1]);
+                if constexpr (TWREG == 2) b = cmul(d1[k1], rq1[k1]);
+                else b = cmul(mul_w64(d1[k1], k1), rq[k1]);
             } else {
                 float4 t = tq[4 * (k1 - 1)];
                 a = cmul(d0[k1], make_float2(t.x, t.y));

@@ -35,7 +35,7 @@ void k1w_build_tables(const float *half_window /* 1024 or nullptr */, float4 *ou
         }
 }
 
-template <int OUT, bool WIN, int WARPS, int MINB, bool TWREG, bool WINREG, int LOAD>
+template <int OUT, bool WIN, int WARPS, int MINB, int TWREG, bool WINREG, int LOAD>
 static cudaError_t launch_v(const K1WParams &p, int grid, cudaStream_t stream, int *occ_out) {
     using G = K1WGeom<WARPS, LOAD == 1>;
     auto kern = k1w_1024_kernel<OUT, WIN, WARPS, MINB, TWREG, WINREG, LOAD>;
@@ -51,24 +51,25 @@ static cudaError_t launch_v(const K1WParams &p, int grid, cudaStream_t stream, i
     return cudaGetLastError();
 }
 
-// variant table: (warps per CTA, min CTAs per SM, twiddles in registers, window in registers, load mode:
+// variant table: (warps per CTA, min CTAs per SM, twiddle registers 0/1/2, window in registers, load mode:
 // 0 LDG, 1 TMA prefetch, 2 LDG register prefetch).  Variant 0 is the production configuration (measured best
 // on B200, profiles/r1_k1w_sweep.md); the others are only compiled with -DKOPEK_K1W_SWEEP for tools/sweep_k1w.py.
+//   windowed:    28 twiddle registers + 32 window registers + 32 prefetch registers (LDG of the next frame)
+//   rectangular: 56 twiddle registers + 32 prefetch registers
+// The TMA landing buffer (load mode 1) costs 27 shared-memory wavefronts per frame on the pipe that bounds the
+// kernel, so it lost to the register prefetch once the register budget allowed both (90.9 % vs 86.9 % burst,
+// 76.9 % vs 73.9 % sustained, Hann).
 #ifdef KOPEK_K1W_SWEEP
 #define KOPEK_K1W_VARIANTS(X)                                                                      \
-    X(0, 4, 3, true, true, 1) X(1, 4, 2, true, true, 2) X(2, 4, 3, true, true, 2)                  \
-    X(3, 4, 2, true, true, 1) X(4, 4, 4, true, true, 1) X(5, 4, 4, true, false, 2)                 \
-    X(6, 2, 5, true, true, 2) X(7, 2, 6, true, true, 1) X(8, 4, 3, true, false, 2)                 \
-    X(9, 4, 3, true, true, 0)
+    X(0, 4, 3, 1, true, 2) X(1, 4, 3, 2, true, 1) X(2, 4, 3, 1, true, 1) X(3, 4, 2, 1, true, 2)    \
+    X(4, 4, 3, 2, true, 2) X(5, 4, 4, 1, true, 1) X(6, 4, 4, 0, true, 2) X(7, 4, 3, 0, true, 2)
 #else
-#define KOPEK_K1W_VARIANTS(X) X(0, 4, 3, true, true, 1)
+#define KOPEK_K1W_VARIANTS(X) X(0, 4, 3, 1, true, 2)
 #endif
-// Variant 0 without a window has 32 registers to spare: the next frame is prefetched into registers
-// (LOAD 2: 93 % of the roofline vs 88.5 % with the TMA landing buffer, profiles/r1_k1w_sweep.md).
 
 template <int OUT, bool WIN>
 static cudaError_t launch_o(const K1WParams &p, int variant, int grid, cudaStream_t stream, int *occ_out) {
-    if (variant == 0 && !WIN) return launch_v<OUT, WIN, 4, 3, true, true, 2>(p, grid, stream, occ_out);
+    if (variant == 0 && !WIN) return launch_v<OUT, WIN, 4, 3, 2, true, 2>(p, grid, stream, occ_out);
     switch (variant) {
 #define X(ID, W, B, T, R, A) case ID: return launch_v<OUT, WIN, W, B, T, R, A>(p, grid, stream, occ_out);
         KOPEK_K1W_VARIANTS(X)
