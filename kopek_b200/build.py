@@ -64,6 +64,8 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     os.makedirs(OBJ, exist_ok=True)
     cc = nvcc()
     extra = ["-Xptxas", "-v"] if ptxas_info else []
+    if os.environ.get("KOPEK_K1_PREF") is not None:   # tuning: force the K1 register prefetch on/off for every size
+        extra.append("-DK1_PREF_ALL=" + ("true" if os.environ["KOPEK_K1_PREF"] == "1" else "false"))
     if os.environ.get("KOPEK_K1W_SWEEP"):      # build every K1W tuning variant (tools/sweep_k1w.py)
         extra.append("-DKOPEK_K1W_SWEEP")
     jobs = []

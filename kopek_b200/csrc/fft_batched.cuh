@@ -93,14 +93,28 @@ template <> struct Dft<16> {
 };
 
 // ---- per-size configuration -------------------------------------------------
+// register prefetch of the next frame group, per size (overridable for tuning runs: -DK1_PREF_ALL=0/1)
+#ifdef K1_PREF_ALL
+#define K1_PREF_256 K1_PREF_ALL
+#define K1_PREF_512 K1_PREF_ALL
+#define K1_PREF_1024 K1_PREF_ALL
+#define K1_PREF_2048 K1_PREF_ALL
+#define K1_PREF_4096 K1_PREF_ALL
+#else   // measured on B200 (profiles/r1_configs.md): +1..4 points at every size
+#define K1_PREF_256 true
+#define K1_PREF_512 true
+#define K1_PREF_1024 true
+#define K1_PREF_2048 true
+#define K1_PREF_4096 true
+#endif
 template <int N_> struct K1Cfg;
 // radices, XOR swizzle q ^ ((q >> SWZ_SHIFT) & SWZ_MASK) and per-frame padding (complex slots) of the exchange
 // buffer -- chosen with tools/bank_check.py (wavefronts within 1.08-1.13x of the conflict-free minimum)
-template <> struct K1Cfg<256>  { static constexpr int S = 2, R0 = 8,  R1 = 16, R2 = 1;  static constexpr int SWZ_SHIFT = 3, SWZ_MASK = 7,  PAD = 8; };
-template <> struct K1Cfg<512>  { static constexpr int S = 2, R0 = 16, R1 = 16, R2 = 1;  static constexpr int SWZ_SHIFT = 4, SWZ_MASK = 15, PAD = 0; };
-template <> struct K1Cfg<1024> { static constexpr int S = 3, R0 = 8,  R1 = 8,  R2 = 8;  static constexpr int SWZ_SHIFT = 3, SWZ_MASK = 15, PAD = 0; };
-template <> struct K1Cfg<2048> { static constexpr int S = 3, R0 = 4,  R1 = 16, R2 = 16; static constexpr int SWZ_SHIFT = 4, SWZ_MASK = 15, PAD = 0; };
-template <> struct K1Cfg<4096> { static constexpr int S = 3, R0 = 8,  R1 = 16, R2 = 16; static constexpr int SWZ_SHIFT = 4, SWZ_MASK = 15, PAD = 0; };
+template <> struct K1Cfg<256>  { static constexpr int S = 2, R0 = 8,  R1 = 16, R2 = 1;  static constexpr int SWZ_SHIFT = 3, SWZ_MASK = 7,  PAD = 8; static constexpr bool PREF = K1_PREF_256; };
+template <> struct K1Cfg<512>  { static constexpr int S = 2, R0 = 16, R1 = 16, R2 = 1;  static constexpr int SWZ_SHIFT = 4, SWZ_MASK = 15, PAD = 0; static constexpr bool PREF = K1_PREF_512; };
+template <> struct K1Cfg<1024> { static constexpr int S = 3, R0 = 8,  R1 = 8,  R2 = 8;  static constexpr int SWZ_SHIFT = 3, SWZ_MASK = 15, PAD = 0; static constexpr bool PREF = K1_PREF_1024; };
+template <> struct K1Cfg<2048> { static constexpr int S = 3, R0 = 4,  R1 = 16, R2 = 16; static constexpr int SWZ_SHIFT = 4, SWZ_MASK = 15, PAD = 0; static constexpr bool PREF = K1_PREF_2048; };
+template <> struct K1Cfg<4096> { static constexpr int S = 3, R0 = 8,  R1 = 16, R2 = 16; static constexpr int SWZ_SHIFT = 4, SWZ_MASK = 15, PAD = 0; static constexpr bool PREF = K1_PREF_4096; };
 
 // Host: fill the M-entry stage-twiddle table of frame size N_ (stage 1 block, then stage 2 block).
 template <int N_> inline void k1_build_stage_twiddles(float2 *out) {
@@ -209,9 +223,12 @@ template <int T> __device__ __forceinline__ void frame_sync() {
     else __syncthreads();
 }
 
+// PREF: the samples of the CTA's NEXT frame group are loaded into registers at the top of the current one
+// (32 registers; pays off where the register budget keeps the occupancy: see K1Cfg<N>::PREF).
 template <int N_, int OUT, bool WIN>
 __global__ void __launch_bounds__(K1Geom<N_>::BLOCK)
 k1_stft_kernel(const K1Params p) {
+    constexpr bool PREF = K1Cfg<N_>::PREF;
     using G = K1Geom<N_>;
     using C = K1Cfg<N_>;
     constexpr int M = G::M, T = G::T, R0 = C::R0, R1 = C::R1, R2 = C::R2;
@@ -232,23 +249,48 @@ k1_stft_kernel(const K1Params p) {
     float2 *buf = s_ex + fslot * G::FSTRIDE;
     const uint64_t n_groups = (p.n_frames + G::FPB - 1) / G::FPB;
 
-    for (uint64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
-        uint64_t frame = g * G::FPB + fslot;
-        const bool valid = frame < p.n_frames;
-        if (!valid) frame = p.n_frames - 1;
-        const float *xf = p.x + frame * p.hop;
-
-        float2 d[16];
-        // ---- stage 0: global load (+ window), butterflies over stride M/R0
+    // samples of frame group gg, slot fslot -> registers (d[i*R0 + t] = z[j + t M/R0], j = tid + T i)
+    auto load_frame = [&](uint64_t gg, float2 *dst) {
+        uint64_t fr = gg * G::FPB + fslot;
+        if (fr >= p.n_frames) fr = p.n_frames - 1;
+        const float *xf = p.x + fr * p.hop;
 #pragma unroll
         for (int i = 0; i < 16 / R0; ++i) {
             int j = tid + T * i;
 #pragma unroll
             for (int t = 0; t < R0; ++t) {
                 int q = j + t * (M / R0);
-                float2 v;
-                if (p.vec) v = __ldg(reinterpret_cast<const float2 *>(xf) + q);
-                else v = make_float2(__ldg(xf + 2 * q), __ldg(xf + 2 * q + 1));
+                if (p.vec) dst[i * R0 + t] = __ldg(reinterpret_cast<const float2 *>(xf) + q);
+                else dst[i * R0 + t] = make_float2(__ldg(xf + 2 * q), __ldg(xf + 2 * q + 1));
+            }
+        }
+    };
+    float2 nx[16];
+    if constexpr (PREF) {
+        if (blockIdx.x < n_groups) load_frame(blockIdx.x, nx);
+    }
+
+    for (uint64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        uint64_t frame = g * G::FPB + fslot;
+        const bool valid = frame < p.n_frames;
+        if (!valid) frame = p.n_frames - 1;
+
+        float2 d[16];
+        if constexpr (PREF) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) d[i] = nx[i];
+            if (g + gridDim.x < n_groups) load_frame(g + gridDim.x, nx);
+        } else {
+            load_frame(g, d);
+        }
+        // ---- stage 0: window, butterflies over stride M/R0
+#pragma unroll
+        for (int i = 0; i < 16 / R0; ++i) {
+            int j = tid + T * i;
+#pragma unroll
+            for (int t = 0; t < R0; ++t) {
+                int q = j + t * (M / R0);
+                float2 v = d[i * R0 + t];
                 if constexpr (WIN) {
                     float2 w = reinterpret_cast<const float2 *>(s_win)[q];
                     v.x *= w.x;
