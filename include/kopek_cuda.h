@@ -139,6 +139,20 @@ KOPEK_API kopek_status kopek_stream_push(kopek_stream *stream, const float *h_sa
 KOPEK_API uint64_t kopek_stream_bins(const kopek_stream *stream);
 KOPEK_API kopek_status kopek_stream_destroy(kopek_stream *stream);
 
+/* ---- 2c. on-device signal sources (src/oscillator.rs:34-91, src/noise.rs:15-21) -------------
+ * Writes n_frames frames of n f32 samples (frame f at d_out + f*stride).  Each frame is one Oscillator
+ * started at phase 0 (Oscillator::new) running at freq0 + freq_step*((first_frame + f) % freq_mod) Hz
+ * (freq_mod 0: every frame at freq0), wave: 0 sine, 1 fake_sine, 2 sawtooth, 3 square(duty), 4 triangle,
+ * 5 silence; the f32 phase-accumulator recurrence of the reference is executed verbatim (the phase
+ * sequence is bit-identical, sinf within 2 ulp of glibc).  noise: 0 none, 1 rand_noise U[-1,1),
+ * 2 white_noise N(0,1), added as value += noise_gain * noise like examples/beep/generator.rs:62-70; the
+ * reference's generator is an unseeded ThreadRng, so only the distribution is reproduced (counter
+ * based, a function of seed and the global sample index: shards generate the same signal). */
+KOPEK_API kopek_status kopek_synth_frames(float *d_out, uint64_t n_frames, uint32_t n, uint64_t stride,
+                                          float sample_rate, uint32_t wave, float duty, float freq0, float freq_step,
+                                          uint32_t freq_mod, uint32_t noise, float noise_gain, uint64_t seed,
+                                          uint64_t first_frame, int device, void *cuda_stream);
+
 /* ---- 3. large single transform (four-step), device-resident c2c f32 ----------
  * Interleaved (re,im) f32, n a power of two with 2^16 <= n <= 2^24, natural-order unnormalised
  * output, d_in != d_out, both 16-byte aligned.  Two HBM passes with TMA-staged tiles; asynchronous

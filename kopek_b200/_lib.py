@@ -45,6 +45,8 @@ SYMBOLS = {
     "kopek_stream_push": (_i32, [_vp, _vp, _u32, _vp]),
     "kopek_stream_bins": (_u64, [_vp]),
     "kopek_stream_destroy": (_i32, [_vp]),
+    "kopek_synth_frames": (_i32, [_vp, _u64, _u32, _u64, C.c_float, _u32, C.c_float, C.c_float, C.c_float, _u32, _u32,
+                                  C.c_float, _u64, _u64, C.c_int, _vp]),
     "kopek_host_alloc": (_i32, [C.POINTER(_vp), _sz]),
     "kopek_host_free": (_i32, [_vp]),
     "kopek_fft_large_c2c_f32": (_i32, [_vp, _vp, _u64, C.c_int, _vp]),

@@ -21,7 +21,7 @@ from . import _lib
 from ._lib import (BAND_ROW, BINS_FULL, BINS_HALF, OUT_BANDS_LOG, OUT_BANDS_LOW, OUT_COMPLEX, OUT_DB, OUT_MAG, OUT_POWER, WINDOW_CUSTOM, WINDOW_HAMMING,
                    WINDOW_HANN, WINDOW_RECT, KopekError, check)
 
-__all__ = ["fft", "fft_batched", "fft_large_device", "LiveSpectrum", "show", "show_format", "StftPlan", "next_pow2", "KopekError",
+__all__ = ["fft", "fft_batched", "fft_large_device", "synth_frames_device", "LiveSpectrum", "show", "show_format", "StftPlan", "next_pow2", "KopekError",
            "WINDOW_RECT", "WINDOW_HANN", "WINDOW_HAMMING", "WINDOW_CUSTOM",
            "OUT_COMPLEX", "OUT_MAG", "OUT_POWER", "OUT_DB", "OUT_BANDS_LOG", "OUT_BANDS_LOW", "BAND_ROW",
            "BINS_HALF", "BINS_FULL"]
@@ -54,6 +54,20 @@ def fft_large_device(d_in: int, d_out: int, n: int, device: int = 0, stream: int
     """Four-step complex f32 FFT of one long device-resident buffer (kopek_fft_large_c2c_f32):
     n interleaved (re,im) pairs at d_in -> n at d_out, natural order, asynchronous on `stream`."""
     check(_lib.load().kopek_fft_large_c2c_f32(d_in, d_out, n, device, stream or None))
+
+
+WAVE_SINE, WAVE_FAKE_SINE, WAVE_SAWTOOTH, WAVE_SQUARE, WAVE_TRIANGLE, WAVE_SILENCE = 0, 1, 2, 3, 4, 5
+NOISE_NONE, NOISE_RANDOM, NOISE_WHITE = 0, 1, 2
+
+
+def synth_frames_device(d_out: int, n_frames: int, n: int, sample_rate: float, wave: int = WAVE_SINE, freq0: float = 440.0,
+                        freq_step: float = 0.0, freq_mod: int = 0, noise: int = NOISE_NONE, noise_gain: float = 1.0,
+                        seed: int = 0, first_frame: int = 0, duty: float = 0.5, stride: int | None = None,
+                        device: int = 0, stream: int = 0) -> None:
+    """kopek_synth_frames: Oscillator (+ Noise) frames generated on the device (src/oscillator.rs, src/noise.rs)."""
+    check(_lib.load().kopek_synth_frames(d_out, n_frames, n, n if stride is None else stride, sample_rate, wave, duty,
+                                         freq0, freq_step, freq_mod, noise, noise_gain, seed, first_frame, device,
+                                         stream or None))
 
 
 def show_format(label: str, buf) -> str:

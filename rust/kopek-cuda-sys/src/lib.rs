@@ -70,6 +70,9 @@ extern "C" {
                              -> kopek_status;
     pub fn kopek_stream_bins(stream: *const kopek_stream) -> u64;
     pub fn kopek_stream_destroy(stream: *mut kopek_stream) -> kopek_status;
+    pub fn kopek_synth_frames(d_out: *mut f32, n_frames: u64, n: u32, stride: u64, sample_rate: f32, wave: u32,
+                              duty: f32, freq0: f32, freq_step: f32, freq_mod: u32, noise: u32, noise_gain: f32,
+                              seed: u64, first_frame: u64, device: c_int, cuda_stream: *mut c_void) -> kopek_status;
     pub fn kopek_host_alloc(ptr: *mut *mut c_void, bytes: usize) -> kopek_status;
     pub fn kopek_host_free(ptr: *mut c_void) -> kopek_status;
 
