@@ -170,18 +170,15 @@ def run_reference(args):
     return 0
 
 
-def make_input(torch, device, frames, first_frame):
-    """Workload M on the device: frame f = sin(2 pi 20 (1 + f mod 1000) t / 48000) + 0.1 N(0,1)."""
-    g = torch.Generator(device=device).manual_seed(1234 + first_frame)
+def make_input(torch, device, frames, first_frame, stream):
+    """Workload M generated on the device by the library's own oscillator/noise sources (kopek_synth_frames):
+    frame f = Oscillator::sine at 20*(1 + f mod 1000) Hz / 48 kHz from phase 0, + 0.1 * N(0,1), seed 1234."""
+    from kopek_b200 import fft
     x = torch.empty(frames * N_FFT, device=device, dtype=torch.float32)
-    t = torch.arange(N_FFT, device=device, dtype=torch.float64) / 48000.0
-    chunk = 1 << 16
-    for f0 in range(0, frames, chunk):
-        f1 = min(frames, f0 + chunk)
-        fr = ((torch.arange(first_frame + f0, first_frame + f1, device=device, dtype=torch.float64) % 1000) + 1.0) * 20.0
-        s = torch.sin(2.0 * torch.pi * fr[:, None] * t[None, :]).to(torch.float32)
-        s += 0.1 * torch.randn((f1 - f0, N_FFT), device=device, generator=g)
-        x[f0 * N_FFT:f1 * N_FFT] = s.reshape(-1)
+    fft.synth_frames_device(x.data_ptr(), frames, N_FFT, 48000.0, wave=fft.WAVE_SINE, freq0=20.0, freq_step=20.0,
+                            freq_mod=1000, noise=fft.NOISE_WHITE, noise_gain=0.1, seed=1234, first_frame=first_frame,
+                            device=device.index or 0, stream=stream)
+    torch.cuda.synchronize()
     return x
 
 
@@ -210,9 +207,9 @@ def run_ours(args):
 
     frames = args.frames
     plan = StftPlan(N_FFT, N_FFT, WINDOW_HANN, OUT_MAG, device=local)
-    x = make_input(torch, device, frames, rank * frames)
-    out = torch.empty((frames, BINS), device=device, dtype=torch.float32)
     stream = torch.cuda.current_stream().cuda_stream
+    x = make_input(torch, device, frames, rank * frames, stream)
+    out = torch.empty((frames, BINS), device=device, dtype=torch.float32)
 
     def step():
         plan.exec_ptr(x.data_ptr(), x.numel(), out.data_ptr(), stream)
