@@ -153,6 +153,20 @@ KOPEK_API kopek_status kopek_synth_frames(float *d_out, uint64_t n_frames, uint3
                                           uint32_t freq_mod, uint32_t noise, float noise_gain, uint64_t seed,
                                           uint64_t first_frame, int device, void *cuda_stream);
 
+/* ---- 2d. peer-direct spectrogram (multi-GPU, one process per GPU) -------------------------------
+ * When the caller wants ONE spectrogram on one GPU, the other ranks do not send their spectra after
+ * the fact: they run kopek_stft_exec with d_out pointing INTO the owner's buffer, mapped through CUDA
+ * IPC, so the epilogue's stores travel over NVLink as they are produced (transform and transfer are
+ * one kernel).  The owner allocates with kopek_device_alloc and exports a 64-byte handle; peers open it. */
+#define KOPEK_IPC_HANDLE_BYTES 64
+KOPEK_API kopek_status kopek_device_alloc(void **d_ptr, size_t bytes, int device);
+KOPEK_API kopek_status kopek_device_free(void *d_ptr, int device);
+/* Copy between any two of host / device / peer-mapped memory (cudaMemcpyDefault), synchronous. */
+KOPEK_API kopek_status kopek_copy(void *dst, const void *src, size_t bytes, int device);
+KOPEK_API kopek_status kopek_ipc_export(const void *d_ptr, unsigned char *handle_out /* 64 bytes */);
+KOPEK_API kopek_status kopek_ipc_open(const unsigned char *handle /* 64 bytes */, int device, void **d_ptr);
+KOPEK_API kopek_status kopek_ipc_close(void *d_ptr, int device);
+
 /* ---- 3. large single transform (four-step), device-resident c2c f32 ----------
  * Interleaved (re,im) f32, n a power of two with 2^16 <= n <= 2^24, natural-order unnormalised
  * output, d_in != d_out, both 16-byte aligned.  Two HBM passes with TMA-staged tiles; asynchronous

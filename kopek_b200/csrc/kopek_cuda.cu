@@ -722,6 +722,55 @@ kopek_status kopek_stream_destroy(kopek_stream *s) {
     return KOPEK_OK;
 }
 
+// ------------------------------------------------------- peer-direct output ----
+kopek_status kopek_device_alloc(void **d_ptr, size_t bytes, int device) {
+    if (!d_ptr) return fail(KOPEK_ERR_INVALID, "d_ptr is NULL");
+    *d_ptr = nullptr;
+    DeviceGuard g(device);
+    if (!g.ok) return fail(KOPEK_ERR_CUDA, "cannot select device %d", device);
+    cudaError_t e = cudaMalloc(d_ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) return fail(KOPEK_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return KOPEK_OK;
+}
+kopek_status kopek_device_free(void *d_ptr, int device) {
+    if (!d_ptr) return KOPEK_OK;
+    DeviceGuard g(device);
+    KOPEK_CUDA(cudaFree(d_ptr));
+    return KOPEK_OK;
+}
+kopek_status kopek_copy(void *dst, const void *src, size_t bytes, int device) {
+    if (!bytes) return KOPEK_OK;
+    if (!dst || !src) return fail(KOPEK_ERR_INVALID, "NULL pointer");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(KOPEK_ERR_CUDA, "cannot select device %d", device);
+    KOPEK_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
+    return KOPEK_OK;
+}
+kopek_status kopek_ipc_export(const void *d_ptr, unsigned char *handle_out) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == KOPEK_IPC_HANDLE_BYTES, "IPC handle size");
+    if (!d_ptr || !handle_out) return fail(KOPEK_ERR_INVALID, "NULL argument");
+    cudaIpcMemHandle_t h;
+    KOPEK_CUDA(cudaIpcGetMemHandle(&h, const_cast<void *>(d_ptr)));
+    memcpy(handle_out, &h, sizeof h);
+    return KOPEK_OK;
+}
+kopek_status kopek_ipc_open(const unsigned char *handle, int device, void **d_ptr) {
+    if (!handle || !d_ptr) return fail(KOPEK_ERR_INVALID, "NULL argument");
+    *d_ptr = nullptr;
+    DeviceGuard g(device);
+    if (!g.ok) return fail(KOPEK_ERR_CUDA, "cannot select device %d", device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    KOPEK_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return KOPEK_OK;
+}
+kopek_status kopek_ipc_close(void *d_ptr, int device) {
+    if (!d_ptr) return KOPEK_OK;
+    DeviceGuard g(device);
+    KOPEK_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return KOPEK_OK;
+}
+
 kopek_status kopek_host_alloc(void **ptr, size_t bytes) {
     if (!ptr) return fail(KOPEK_ERR_INVALID, "ptr is NULL");
     *ptr = nullptr;

@@ -45,16 +45,73 @@ def gather_spectra(local, n_frames_total: int, dst: int = 0, group=None):
         return local
     if rank == dst:
         full = torch.empty((n_frames_total, local.shape[1]), dtype=local.dtype, device=local.device)
-        reqs = []
+        ops = []
         for r in range(world):
             f0, f1 = frame_range(r, world, n_frames_total)
             if r == dst:
                 full[f0:f1].copy_(local)
             elif f1 > f0:
-                reqs.append(dist.irecv(full[f0:f1], src=r, group=group))
-        for q in reqs:
-            q.wait()
+                ops.append(dist.P2POp(dist.irecv, full[f0:f1], r, group))
+        if ops:                                   # one grouped launch (ncclGroupStart/End): the receives overlap
+            for q in dist.batch_isend_irecv(ops):
+                q.wait()
         return full
     if local.shape[0] > 0:
-        dist.isend(local.contiguous(), dst=dst, group=group).wait()
+        for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, local.contiguous(), dst, group)]):
+            q.wait()
     return None
+
+
+class PeerSpectrogram:
+    """One [n_frames_total, pitch] spectrogram on `dst`'s GPU that every rank's kernel writes into directly.
+
+    `dst` allocates the buffer (kopek_device_alloc) and broadcasts its CUDA IPC handle; the other ranks map it
+    (kopek_ipc_open) and pass `row_ptr(f0)` as d_out of StftPlan.exec_ptr, so K1/K1W store their bins straight
+    into the owner's HBM over NVLink -- transform and transfer are one kernel, no gather afterwards.
+    Call `finish()` (device sync + barrier) before the owner reads; `to_host()` / `copy_to(ptr)` on the owner.
+    """
+
+    def __init__(self, n_frames_total: int, pitch: int, elem_bytes: int, local_device: int, dst: int = 0, group=None):
+        import ctypes as C
+
+        import torch.distributed as dist
+
+        from . import _lib
+        self._lib, self._check, self._C = _lib.load(), _lib.check, C
+        self.frames, self.pitch, self.elem_bytes, self.device = n_frames_total, pitch, elem_bytes, local_device
+        self.group, self.dst = group, dst
+        self.rank = dist.get_rank(group)
+        self.nbytes = n_frames_total * pitch * elem_bytes
+        self._ptr = C.c_void_p()
+        handle = [None]
+        if self.rank == dst:
+            self._check(self._lib.kopek_device_alloc(C.byref(self._ptr), self.nbytes, local_device))
+            raw = (C.c_ubyte * 64)()
+            self._check(self._lib.kopek_ipc_export(self._ptr, raw))
+            handle = [bytes(raw)]
+        dist.broadcast_object_list(handle, src=dst, group=group)
+        if self.rank != dst:
+            raw = (C.c_ubyte * 64).from_buffer_copy(handle[0])
+            self._check(self._lib.kopek_ipc_open(raw, local_device, C.byref(self._ptr)))
+
+    def row_ptr(self, frame: int) -> int:
+        return self._ptr.value + frame * self.pitch * self.elem_bytes
+
+    def finish(self) -> None:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize(self.device)        # this rank's peer stores have left the SMs and are visible
+        dist.barrier(group=self.group)
+
+    def copy_to(self, dst_ptr: int) -> None:
+        """Owner only: copy the finished spectrogram to a host or device pointer."""
+        assert self.rank == self.dst
+        self._check(self._lib.kopek_copy(dst_ptr, self._ptr, self.nbytes, self.device))
+
+    def close(self) -> None:
+        if self._ptr:
+            if self.rank == self.dst:
+                self._lib.kopek_device_free(self._ptr, self.device)
+            else:
+                self._lib.kopek_ipc_close(self._ptr, self.device)
+            self._ptr = self._C.c_void_p()

@@ -73,6 +73,12 @@ extern "C" {
     pub fn kopek_synth_frames(d_out: *mut f32, n_frames: u64, n: u32, stride: u64, sample_rate: f32, wave: u32,
                               duty: f32, freq0: f32, freq_step: f32, freq_mod: u32, noise: u32, noise_gain: f32,
                               seed: u64, first_frame: u64, device: c_int, cuda_stream: *mut c_void) -> kopek_status;
+    pub fn kopek_device_alloc(d_ptr: *mut *mut c_void, bytes: usize, device: c_int) -> kopek_status;
+    pub fn kopek_device_free(d_ptr: *mut c_void, device: c_int) -> kopek_status;
+    pub fn kopek_copy(dst: *mut c_void, src: *const c_void, bytes: usize, device: c_int) -> kopek_status;
+    pub fn kopek_ipc_export(d_ptr: *const c_void, handle_out: *mut u8) -> kopek_status;
+    pub fn kopek_ipc_open(handle: *const u8, device: c_int, d_ptr: *mut *mut c_void) -> kopek_status;
+    pub fn kopek_ipc_close(d_ptr: *mut c_void, device: c_int) -> kopek_status;
     pub fn kopek_host_alloc(ptr: *mut *mut c_void, bytes: usize) -> kopek_status;
     pub fn kopek_host_free(ptr: *mut c_void) -> kopek_status;
 

@@ -36,6 +36,22 @@ with StftPlan(n, hop, WINDOW_HANN, OUT_MAG, device=local) as plan:
         torch.cuda.synchronize()
         assert full.shape == ref.shape and torch.equal(full, ref)      # shards are bit-identical to the 1-GPU run
         print("SHARDED_OK", world, frames)
+    # peer-direct: every rank's kernel stores straight into rank 0's buffer over NVLink (no gather afterwards)
+    from kopek_b200.sharded import PeerSpectrogram
+    peer = PeerSpectrogram(frames, plan.pitch, plan.elem_bytes, local, dst=0)
+    assert plan.exec_ptr(d.data_ptr(), d.numel(), peer.row_ptr(f0), st) == f1 - f0
+    peer.finish()
+    if rank == 0:
+        got = torch.empty((frames, plan.pitch), device="cuda")
+        peer.copy_to(got.data_ptr())
+        assert torch.equal(got[:, :plan.bins], ref)
+        print("PEER_DIRECT_OK")
+    dist.barrier()
+    if rank != 0:
+        peer.close()
+    dist.barrier()
+    if rank == 0:
+        peer.close()
 dist.barrier()
 dist.destroy_process_group()
 '''
@@ -52,4 +68,4 @@ def test_sharded_stft_gather_nccl(built_lib, tmp_path):
            "--master-addr", "127.0.0.1", "--master-port", str(29700 + os.getpid() % 200), str(script), ROOT]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert "SHARDED_OK" in r.stdout
+    assert "SHARDED_OK" in r.stdout and "PEER_DIRECT_OK" in r.stdout
