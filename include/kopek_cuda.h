@@ -101,6 +101,11 @@ KOPEK_API kopek_status kopek_show(const char *label, const double *buf, size_t n
 typedef struct kopek_plan kopek_plan;
 KOPEK_API kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint32_t window,
                                          uint32_t output, uint32_t bins, uint64_t out_pitch_elems, int device);
+/* Opt-in epilogue for n = 1024 f32 spectra with 16-byte aligned rows (out_pitch_elems % 4 == 0, e.g. 516): each
+ * frame leaves the SM as one 2048-byte bulk (TMA) store + one word instead of 32-bit stores.  Same speed on
+ * local HBM; over NVLink (d_out mapped from a peer GPU, section 2d) it is what reaches link bandwidth.
+ * Falls back to the direct stores when d_out is not 16-byte aligned. */
+KOPEK_API kopek_status kopek_plan_set_bulk_store(kopek_plan *plan, int enable);
 /* Display scale of the band epilogues (KOPEK_OUT_BANDS_*); takes effect at the next execute. */
 KOPEK_API kopek_status kopek_plan_set_band_scale(kopek_plan *plan, float scale);
 /* Replace the window by n caller-supplied f32 coefficients (host pointer). */

@@ -33,6 +33,7 @@ SYMBOLS = {
     "kopek_plan_create": (_i32, [C.POINTER(_vp), _u32, _u32, _u32, _u32, _u32, _u64, C.c_int]),
     "kopek_plan_set_window": (_i32, [_vp, _vp]),
     "kopek_plan_set_band_scale": (_i32, [_vp, C.c_float]),
+    "kopek_plan_set_bulk_store": (_i32, [_vp, C.c_int]),
     "kopek_plan_destroy": (_i32, [_vp]),
     "kopek_plan_frames": (_u64, [_vp, _u64]),
     "kopek_plan_bins": (_u64, [_vp]),

@@ -44,9 +44,11 @@ constexpr int K1W_EX_F4 = 288;             // per-warp exchange buffer: 256 slot
 
 constexpr int K1W_IN_F4 = 256;             // per-warp TMA landing buffer: one frame, linear
 
-template <int WARPS, bool TMA = false> struct K1WGeom {
+constexpr int K1W_STAGE_F4 = 132;          // per-warp output staging of the bulk-store epilogue (516 floats + pad)
+
+template <int WARPS, bool TMA = false, bool BULK = false> struct K1WGeom {
     static constexpr int BLOCK = WARPS * 32;
-    static constexpr int WARP_F4 = K1W_EX_F4 + (TMA ? K1W_IN_F4 : 0);
+    static constexpr int WARP_F4 = K1W_EX_F4 + (TMA ? K1W_IN_F4 : 0) + (BULK ? K1W_STAGE_F4 : 0);
     // tables | per-warp (exchange [+ landing]) | per-warp mbarrier
     static constexpr size_t SMEM = sizeof(float4) * (K1W_TABLE_F4 + WARPS * WARP_F4) + (TMA ? 8 * WARPS : 0);
 };
@@ -139,10 +141,15 @@ __device__ __forceinline__ float2 mul_w1024_off(float2 a, int idx) {
 //      the current one is transformed (the buffer is free as soon as pass A has read it).
 // LOAD: 0 = plain LDG.128 at the top of the frame, 1 = TMA prefetch (above), 2 = LDG.128 of the next frame
 //       into registers at the top of the current one (no shared-memory landing traffic, 32 more registers).
-template <int OUT, bool WIN, int WARPS, int MINB, int TWREG, bool WINREG, int LOAD>
+// BULK (f32 outputs, rows 16-byte aligned: pitch % 4 == 0): the frame's 513 values are staged in the warp's exchange
+//       buffer and leave as ONE cp.async.bulk store of 2048 bytes (+ bin 512) instead of 17 32-bit stores per lane.
+//       On local HBM the direct stores are as fast; over NVLink (peer-direct spectrogram, kopek_b200/sharded.py) the
+//       bulk store is what reaches link bandwidth.
+template <int OUT, bool WIN, int WARPS, int MINB, int TWREG, bool WINREG, int LOAD, bool BULK = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 k1w_1024_kernel(const K1WParams p) {
     constexpr int M = 512;
+    static_assert(!BULK || (OUT == OUT_MAG || OUT == OUT_POWER || OUT == OUT_DB), "bulk store: f32 spectra only");
     constexpr bool TMA = LOAD == 1;
     extern __shared__ __align__(16) unsigned char k1w_smem[];
     float4 *s_win = reinterpret_cast<float4 *>(k1w_smem);
@@ -155,9 +162,9 @@ k1w_1024_kernel(const K1WParams p) {
     __syncthreads();
 
     const int l = threadIdx.x & 31;
-    float4 *ex = s_ex + (threadIdx.x >> 5) * K1WGeom<WARPS, TMA>::WARP_F4;
+    float4 *ex = s_ex + (threadIdx.x >> 5) * K1WGeom<WARPS, TMA, BULK>::WARP_F4;
     const float4 *in = ex + K1W_EX_F4 + l;                   // TMA landing buffer, + 32 n2
-    uint64_t *bar = reinterpret_cast<uint64_t *>(s_ex + WARPS * K1WGeom<WARPS, TMA>::WARP_F4) + (threadIdx.x >> 5);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(s_ex + WARPS * K1WGeom<WARPS, TMA, BULK>::WARP_F4) + (threadIdx.x >> 5);
     uint32_t phase = 0;
     float4 *exA = ex + l + (l >> 3);                         // + 36 k2
     float4 *exB = ex + 36 * (l >> 2) + (l & 3);              // + 4 n1 + (n1 >> 1)
@@ -334,6 +341,15 @@ k1w_1024_kernel(const K1WParams p) {
         constexpr int EB = OUT == OUT_COMPLEX ? 8 : 4;
         char *o_lo = reinterpret_cast<char *>(p.out) + (frame * p.pitch + kbase) * EB;
         char *o_hi = reinterpret_cast<char *>(p.out) + (frame * p.pitch + (M - kbase)) * EB;
+        // BULK: the warp's own staging buffer (never aliased by the exchange passes of the next frame, which start
+        // while the TMA engine may still be reading this frame's row)
+        float *stage = reinterpret_cast<float *>(ex + K1W_EX_F4 + (TMA ? K1W_IN_F4 : 0));
+        if constexpr (BULK) {
+            if (l == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous frame has left
+            __syncwarp();
+            o_lo = reinterpret_cast<char *>(stage + kbase);
+            o_hi = reinterpret_cast<char *>(stage + (M - kbase));
+        }
 #pragma unroll
         for (int k0 = 0; k0 < 4; ++k0) {
 #pragma unroll
@@ -394,8 +410,22 @@ k1w_1024_kernel(const K1WParams p) {
             }
         } else {
             if (l == 0) emit_at<OUT, WIN>(o_lo + (M / 2) * EB, make_float2(2.0f * d0[4].x, -2.0f * d0[4].y));
+            if constexpr (BULK) {
+                __syncwarp();
+                if (l == 0) {
+                    float *row = reinterpret_cast<float *>(p.out) + frame * p.pitch;
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 2048;" ::"l"(row),
+                                 "r"(smem_u32(stage)) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    row[M] = stage[M];                             // bin 512: the 513th value of the row
+                }
+            }
         }
         __syncwarp();
+    }
+    if constexpr (BULK) {
+        if (l == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 }
 

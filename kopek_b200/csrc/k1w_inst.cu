@@ -35,10 +35,10 @@ void k1w_build_tables(const float *half_window /* 1024 or nullptr */, float4 *ou
         }
 }
 
-template <int OUT, bool WIN, int WARPS, int MINB, int TWREG, bool WINREG, int LOAD>
+template <int OUT, bool WIN, int WARPS, int MINB, int TWREG, bool WINREG, int LOAD, bool BULK = false>
 static cudaError_t launch_v(const K1WParams &p, int grid, cudaStream_t stream, int *occ_out) {
-    using G = K1WGeom<WARPS, LOAD == 1>;
-    auto kern = k1w_1024_kernel<OUT, WIN, WARPS, MINB, TWREG, WINREG, LOAD>;
+    using G = K1WGeom<WARPS, LOAD == 1, BULK>;
+    auto kern = k1w_1024_kernel<OUT, WIN, WARPS, MINB, TWREG, WINREG, LOAD, BULK>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
     if (e != cudaSuccess) return e;
     if (occ_out) {
@@ -69,6 +69,12 @@ static cudaError_t launch_v(const K1WParams &p, int grid, cudaStream_t stream, i
 
 template <int OUT, bool WIN>
 static cudaError_t launch_o(const K1WParams &p, int variant, int grid, cudaStream_t stream, int *occ_out) {
+    if constexpr (OUT == OUT_MAG || OUT == OUT_POWER || OUT == OUT_DB) {
+        if (variant == 100) {      // production shape with the bulk-store epilogue (kopek_plan_set_bulk_store)
+            if (WIN) return launch_v<OUT, WIN, 4, 3, 1, true, 2, true>(p, grid, stream, occ_out);
+            return launch_v<OUT, WIN, 4, 3, 2, true, 2, true>(p, grid, stream, occ_out);
+        }
+    }
     if (variant == 0 && !WIN) return launch_v<OUT, WIN, 4, 3, 2, true, 2>(p, grid, stream, occ_out);
     switch (variant) {
 #define X(ID, W, B, T, R, A) case ID: return launch_v<OUT, WIN, W, B, T, R, A>(p, grid, stream, occ_out);
@@ -79,6 +85,7 @@ static cudaError_t launch_o(const K1WParams &p, int variant, int grid, cudaStrea
 }
 
 int k1w_variant_warps(int variant) {
+    if (variant == 100) return 4;
     switch (variant) {
 #define X(ID, W, B, T, R, A) case ID: return W;
         KOPEK_K1W_VARIANTS(X)

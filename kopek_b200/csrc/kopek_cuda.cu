@@ -233,6 +233,7 @@ struct kopek_plan {
     float4 *d_k1w;     // tables of the warp-per-frame kernel (n == 1024 only)
     int k1w_variant, k1w_warps_per_sm;
     float band_scale;
+    int bulk_store;
     mutable uint32_t last_launches;
     // exec_host resources (lazy)
     std::mutex mu;
@@ -397,7 +398,7 @@ kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint
     p->bins = nb; p->pitch = out_pitch_elems; p->elem_bytes = output == KOPEK_OUT_COMPLEX ? 8 : 4;
     p->device = device; p->launch = launch; p->info = info();
     p->d_win = nullptr; p->d_tw = nullptr; p->d_pw = nullptr; p->last_launches = 0; p->slot_frames = 0;
-    p->d_k1w = nullptr; p->k1w_variant = 0; p->k1w_warps_per_sm = 0; p->band_scale = 1.0f;
+    p->d_k1w = nullptr; p->k1w_variant = 0; p->k1w_warps_per_sm = 0; p->band_scale = 1.0f; p->bulk_store = 0;
 
     kopek_status st = KOPEK_OK;
     do {
@@ -475,6 +476,16 @@ kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint
     return KOPEK_OK;
 }
 
+kopek_status kopek_plan_set_bulk_store(kopek_plan *plan, int enable) {
+    if (!plan) return fail(KOPEK_ERR_INVALID, "plan is NULL");
+    if (enable && (plan->n != 1024 || plan->pitch % 4 != 0 || plan->output < KOPEK_OUT_MAG || plan->output > KOPEK_OUT_DB ||
+                   plan->bins_mode != KOPEK_BINS_HALF))
+        return fail(KOPEK_ERR_UNSUPPORTED, "bulk store needs n = 1024, HALF bins, an f32 output (MAG/POWER/DB) and "
+                                           "out_pitch_elems %% 4 == 0 (e.g. 516)");
+    plan->bulk_store = enable ? 1 : 0;
+    return KOPEK_OK;
+}
+
 kopek_status kopek_plan_set_band_scale(kopek_plan *plan, float scale) {
     if (!plan) return fail(KOPEK_ERR_INVALID, "plan is NULL");
     plan->band_scale = scale;
@@ -522,11 +533,15 @@ static kopek_status stft_launch(const kopek_plan *plan, const float *d_samples, 
         wp.hop = plan->hop;
         wp.pitch = plan->pitch;
         wp.band_scale = plan->band_scale;
+        // bulk-store epilogue: opt-in, f32 spectra, 16-byte aligned rows (else the direct 32-bit stores)
+        const bool bulk = plan->bulk_store && plan->output >= KOPEK_OUT_MAG && plan->output <= KOPEK_OUT_DB &&
+                          plan->pitch % 4 == 0 && (uintptr_t)d_out % 16 == 0;
+        const int variant = bulk ? 100 : plan->k1w_variant;
         const uint64_t warps = (uint64_t)plan->sm_count * plan->k1w_warps_per_sm;
-        const int wpb = k1w_variant_warps(plan->k1w_variant);
+        const int wpb = k1w_variant_warps(variant);
         const int grid = (int)std::min<uint64_t>((frames + wpb - 1) / wpb, warps / wpb);
-        cudaError_t e = k1w_launch(wp, (int)plan->output, plan->window != KOPEK_WINDOW_RECT, plan->k1w_variant, grid,
-                                   stream, nullptr);
+        cudaError_t e = k1w_launch(wp, (int)plan->output, plan->window != KOPEK_WINDOW_RECT, variant, grid, stream,
+                                   nullptr);
         if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "K1W launch failed: %s", cudaGetErrorString(e));
         return KOPEK_OK;
     }

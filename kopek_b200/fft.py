@@ -90,7 +90,7 @@ class StftPlan:
 
     def __init__(self, n: int, hop: int | None = None, window: int = WINDOW_RECT, output: int = OUT_MAG,
                  bins: int = BINS_HALF, out_pitch: int = 0, device: int = 0, custom_window=None,
-                 band_scale: float | None = None):
+                 band_scale: float | None = None, bulk_store: bool = False):
         self._h = C.c_void_p()
         self._lib = _lib.load()
         hop = n if hop is None else hop
@@ -99,6 +99,8 @@ class StftPlan:
         self.bins = int(self._lib.kopek_plan_bins(self._h))
         self.pitch = int(self._lib.kopek_plan_out_pitch(self._h))
         self.elem_bytes = int(self._lib.kopek_plan_out_elem_bytes(self._h))
+        if bulk_store:
+            check(self._lib.kopek_plan_set_bulk_store(self._h, 1))
         if band_scale is not None:
             check(self._lib.kopek_plan_set_band_scale(self._h, band_scale))
         if custom_window is not None:

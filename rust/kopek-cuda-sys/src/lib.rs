@@ -54,6 +54,7 @@ extern "C" {
                              out_pitch_elems: u64, device: c_int) -> kopek_status;
     pub fn kopek_plan_set_window(plan: *mut kopek_plan, window_host: *const f32) -> kopek_status;
     pub fn kopek_plan_set_band_scale(plan: *mut kopek_plan, scale: f32) -> kopek_status;
+    pub fn kopek_plan_set_bulk_store(plan: *mut kopek_plan, enable: c_int) -> kopek_status;
     pub fn kopek_plan_destroy(plan: *mut kopek_plan) -> kopek_status;
     pub fn kopek_plan_frames(plan: *const kopek_plan, n_samples: u64) -> u64;
     pub fn kopek_plan_bins(plan: *const kopek_plan) -> u64;

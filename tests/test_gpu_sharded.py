@@ -52,6 +52,22 @@ with StftPlan(n, hop, WINDOW_HANN, OUT_MAG, device=local) as plan:
     dist.barrier()
     if rank == 0:
         peer.close()
+# the same with 16-byte aligned rows and the bulk-store epilogue (one TMA store per frame crosses NVLink)
+with StftPlan(n, hop, WINDOW_HANN, OUT_MAG, out_pitch=516, device=local, bulk_store=True) as bplan:
+    peer = PeerSpectrogram(frames, 516, 4, local, dst=0)
+    assert bplan.exec_ptr(d.data_ptr(), d.numel(), peer.row_ptr(f0), st) == f1 - f0
+    peer.finish()
+    if rank == 0:
+        got = torch.empty((frames, 516), device="cuda")
+        peer.copy_to(got.data_ptr())
+        assert torch.equal(got[:, :513], ref)
+        print("PEER_BULK_OK")
+    dist.barrier()
+    if rank != 0:
+        peer.close()
+    dist.barrier()
+    if rank == 0:
+        peer.close()
 dist.barrier()
 dist.destroy_process_group()
 '''
@@ -68,4 +84,4 @@ def test_sharded_stft_gather_nccl(built_lib, tmp_path):
            "--master-addr", "127.0.0.1", "--master-port", str(29700 + os.getpid() % 200), str(script), ROOT]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert "SHARDED_OK" in r.stdout and "PEER_DIRECT_OK" in r.stdout
+    assert "SHARDED_OK" in r.stdout and "PEER_DIRECT_OK" in r.stdout and "PEER_BULK_OK" in r.stdout

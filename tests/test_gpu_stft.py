@@ -221,3 +221,34 @@ def test_full_size_properties(built_lib):
         ref = torch.fft.rfft(x.view(frames, n)[:4096].double(), dim=1)
         err = (fx[:4096].to(torch.complex128) - ref).abs().amax(1) / ref.abs().amax(1)
         assert err.max().item() <= tol(n)
+
+
+@pytest.mark.parametrize("window,output", [(1, 1), (0, 3), (2, 2)])
+def test_bulk_store_epilogue_is_bit_identical(built_lib, window, output):
+    """kopek_plan_set_bulk_store: one 2048-byte TMA store per frame instead of 32-bit stores -- same bits, padding untouched."""
+    import torch
+    from kopek_b200 import StftPlan, KopekError
+    n, frames = 1024, 3001
+    x = torch.randn(frames * n, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    ref_plan = StftPlan(n, n, window, output, out_pitch=516)
+    bulk_plan = StftPlan(n, n, window, output, out_pitch=516, bulk_store=True)
+    if True:
+        a = torch.full((frames, 516), float("nan"), device="cuda")
+        b = torch.full((frames, 516), float("nan"), device="cuda")
+        ref_plan.exec_ptr(x.data_ptr(), x.numel(), a.data_ptr(), st)
+        bulk_plan.exec_ptr(x.data_ptr(), x.numel(), b.data_ptr(), st)
+        torch.cuda.synchronize()
+        assert torch.equal(a[:, :513], b[:, :513])
+        assert bool(torch.isnan(b[:, 513:]).all()) and not bool(torch.isnan(b[:, :513]).any())
+        # unaligned output pointer -> silently the direct stores, still correct
+        c = torch.full((frames * 516 + 1,), float("nan"), device="cuda")
+        bulk_plan.exec_ptr(x.data_ptr(), x.numel(), c.data_ptr() + 4, st)
+        torch.cuda.synchronize()
+        assert torch.equal(c[1:].view(frames, 516)[:, :513], a[:, :513])
+    ref_plan.close()
+    bulk_plan.close()
+    with pytest.raises(KopekError):
+        StftPlan(n, n, window, output, bulk_store=True)            # pitch 513: rows not 16-byte aligned
+    with pytest.raises(KopekError):
+        StftPlan(512, 512, window, output, out_pitch=260, bulk_store=True)
