@@ -4,6 +4,7 @@
 #include <vector>
 
 #include "k1w_launch.cuh"
+#include "fft_warp256.cuh"
 
 namespace kopek {
 
@@ -109,6 +110,55 @@ cudaError_t k1w_launch(const K1WParams &p, int output, bool win, int variant, in
         case 9: return launch_o<OUT_BANDS_LOG, true>(p, variant, grid, stream, occ_out);
         case 10: return launch_o<OUT_BANDS_LOW, false>(p, variant, grid, stream, occ_out);
         default: return launch_o<OUT_BANDS_LOW, true>(p, variant, grid, stream, occ_out);
+    }
+}
+
+// ------------------------------------------------------------------ 256-point, eight lanes per frame ----
+void k1w256_build_tables(const float *half_window /* 256 or nullptr */, float4 *out) {
+    const double tau = 2.0 * M_PI;
+    for (int i = 0; i < K256_WIN_F4; ++i)
+        out[i] = half_window ? make_float4(half_window[4 * i], half_window[4 * i + 1], half_window[4 * i + 2],
+                                           half_window[4 * i + 3])
+                             : make_float4(0.5f, 0.5f, 0.5f, 0.5f);
+    float4 *tw = out + K256_WIN_F4;
+    for (int k1 = 1; k1 < 8; ++k1)
+        for (int a = 0; a < 8; ++a) {
+            double x = -tau * (double)(2 * a * k1) / 128.0, y = -tau * (double)((2 * a + 1) * k1) / 128.0;
+            tw[(k1 - 1) * 8 + a] = make_float4((float)cos(x), (float)sin(x), (float)cos(y), (float)sin(y));
+        }
+    float4 *pw = tw + K256_TW_F4;
+    for (int a = 0; a < 8; ++a) {
+        double x = tau * (double)a / 256.0;
+        pw[a] = make_float4((float)-sin(x), (float)-cos(x), 0.0f, 0.0f);
+    }
+}
+
+template <int OUT, bool WIN>
+static cudaError_t launch256(const K1WParams &p, int grid, cudaStream_t stream, int *occ_out) {
+    constexpr int WARPS = 4;
+    auto kern = k1w_256_kernel<OUT, WIN, WARPS, 3>;
+    constexpr size_t smem = sizeof(float4) * WARPS * K256_EX_F4;
+    if (occ_out) {
+        int nb = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, WARPS * 32, smem);
+        *occ_out = nb * WARPS;
+        return e;
+    }
+    kern<<<grid, WARPS * 32, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t k1w256_launch(const K1WParams &p, int output, bool win, int grid, cudaStream_t stream, int *occ_out) {
+    switch (output * 2 + (win ? 1 : 0)) {
+        case 0: return launch256<OUT_COMPLEX, false>(p, grid, stream, occ_out);
+        case 1: return launch256<OUT_COMPLEX, true>(p, grid, stream, occ_out);
+        case 2: return launch256<OUT_MAG, false>(p, grid, stream, occ_out);
+        case 3: return launch256<OUT_MAG, true>(p, grid, stream, occ_out);
+        case 4: return launch256<OUT_POWER, false>(p, grid, stream, occ_out);
+        case 5: return launch256<OUT_POWER, true>(p, grid, stream, occ_out);
+        case 6: return launch256<OUT_DB, false>(p, grid, stream, occ_out);
+        case 7: return launch256<OUT_DB, true>(p, grid, stream, occ_out);
+        default: return cudaErrorInvalidValue;
     }
 }
 

@@ -258,10 +258,14 @@ static kopek_status upload_window(kopek_plan *p, const float *w) {
     for (uint32_t i = 0; i < p->n; ++i) half[i] = 0.5f * w[i];
     if (!p->d_win) KOPEK_CUDA(cudaMalloc(&p->d_win, p->n * sizeof(float)));
     KOPEK_CUDA(cudaMemcpy(p->d_win, half.data(), p->n * sizeof(float), cudaMemcpyHostToDevice));
-    if (p->d_k1w) {
+    if (p->d_k1w && p->n == 1024) {
         std::vector<float4> t(K1W_TABLE_F4);
         k1w_build_tables(half.data(), t.data());
         KOPEK_CUDA(cudaMemcpy(p->d_k1w, t.data(), sizeof(float4) * K1W_TABLE_F4, cudaMemcpyHostToDevice));
+    } else if (p->d_k1w && p->n == 256) {
+        std::vector<float4> t(K1W256_TABLE_F4);
+        k1w256_build_tables(half.data(), t.data());
+        KOPEK_CUDA(cudaMemcpy(p->d_k1w, t.data(), sizeof(float4) * K1W256_TABLE_F4, cudaMemcpyHostToDevice));
     }
     return KOPEK_OK;
 }
@@ -458,6 +462,26 @@ kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint
                 }
             }
         }
+        if (n == 256 && output <= KOPEK_OUT_DB) {
+            // configs[2] size: eight-lanes-per-frame kernel (fft_warp256.cuh); K1 stays for FULL bins / odd hops
+            const char *env = getenv("KOPEK_K1W_VARIANT");
+            if (!(env && atoi(env) < 0)) {
+                std::vector<float4> t(K1W256_TABLE_F4);
+                k1w256_build_tables(nullptr, t.data());
+                if ((e = cudaMalloc(&p->d_k1w, sizeof(float4) * K1W256_TABLE_F4)) != cudaSuccess ||
+                    (e = cudaMemcpy(p->d_k1w, t.data(), sizeof(float4) * K1W256_TABLE_F4, cudaMemcpyHostToDevice)) !=
+                        cudaSuccess) {
+                    st = fail(KOPEK_ERR_CUDA, "K1W-256 table upload failed: %s", cudaGetErrorString(e));
+                    break;
+                }
+                K1WParams dummy{};
+                e = k1w256_launch(dummy, (int)output, window != KOPEK_WINDOW_RECT, 0, nullptr, &p->k1w_warps_per_sm);
+                if (e != cudaSuccess || p->k1w_warps_per_sm <= 0) {
+                    st = fail(KOPEK_ERR_CUDA, "K1W-256 kernel cannot be resident: %s", cudaGetErrorString(e));
+                    break;
+                }
+            }
+        }
         if (window == KOPEK_WINDOW_HANN || window == KOPEK_WINDOW_HAMMING) {
             std::vector<float> w;
             host_window(window, n, w);
@@ -524,7 +548,25 @@ static kopek_status stft_launch(const kopek_plan *plan, const float *d_samples, 
                                 cudaStream_t stream) {
     if (plan->output >= KOPEK_OUT_BANDS_LOG && (uintptr_t)d_samples % 16 != 0)
         return fail(KOPEK_ERR_INVALID, "band epilogues need a 16-byte aligned sample buffer");
-    if (plan->d_k1w && plan->bins_mode == KOPEK_BINS_HALF && plan->hop % 4 == 0 && (uintptr_t)d_samples % 16 == 0) {
+    if (plan->d_k1w && plan->n == 256 && plan->bins_mode == KOPEK_BINS_HALF && plan->hop % 4 == 0 &&
+        (uintptr_t)d_samples % 16 == 0) {
+        K1WParams wp;
+        wp.x = d_samples;
+        wp.out = d_out;
+        wp.tables = plan->d_k1w;
+        wp.n_frames = frames;
+        wp.hop = plan->hop;
+        wp.pitch = plan->pitch;
+        wp.band_scale = 1.0f;
+        const uint64_t groups = (frames + 3) / 4;                 // four frames per warp
+        const uint64_t warps = (uint64_t)plan->sm_count * plan->k1w_warps_per_sm;
+        const int grid = (int)std::min<uint64_t>((groups + 3) / 4, warps / 4);
+        cudaError_t e = k1w256_launch(wp, (int)plan->output, plan->window != KOPEK_WINDOW_RECT, grid, stream, nullptr);
+        if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "K1W-256 launch failed: %s", cudaGetErrorString(e));
+        return KOPEK_OK;
+    }
+    if (plan->d_k1w && plan->n == 1024 && plan->bins_mode == KOPEK_BINS_HALF && plan->hop % 4 == 0 &&
+        (uintptr_t)d_samples % 16 == 0) {
         K1WParams wp;
         wp.x = d_samples;
         wp.out = d_out;
