@@ -4,7 +4,7 @@
 #include <vector>
 
 #include "k1w_launch.cuh"
-#include "fft_warp256.cuh"
+#include "fft_warp512.cuh"
 
 namespace kopek {
 
@@ -158,6 +158,54 @@ cudaError_t k1w256_launch(const K1WParams &p, int output, bool win, int grid, cu
         case 5: return launch256<OUT_POWER, true>(p, grid, stream, occ_out);
         case 6: return launch256<OUT_DB, false>(p, grid, stream, occ_out);
         case 7: return launch256<OUT_DB, true>(p, grid, stream, occ_out);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// ------------------------------------------------------------------ 512-point, sixteen lanes per frame ----
+void k1w512_build_tables(const float *half_window /* 512 or nullptr */, float4 *out4) {
+    float2 *out = reinterpret_cast<float2 *>(out4);
+    const double tau = 2.0 * M_PI;
+    for (int i = 0; i < K512_WIN_F2; ++i)
+        out[i] = half_window ? make_float2(half_window[2 * i], half_window[2 * i + 1]) : make_float2(0.5f, 0.5f);
+    float2 *tw = out + K512_WIN_F2;
+    for (int k1 = 1; k1 < 16; ++k1)
+        for (int a = 0; a < 16; ++a) {
+            double x = -tau * (double)(a * k1) / 256.0;
+            tw[(k1 - 1) * 16 + a] = make_float2((float)cos(x), (float)sin(x));
+        }
+    float2 *pw = tw + K512_TW_F2;
+    for (int a = 0; a < 16; ++a) {
+        double x = tau * (double)a / 512.0;
+        pw[a] = make_float2((float)-sin(x), (float)-cos(x));
+    }
+}
+
+template <int OUT, bool WIN>
+static cudaError_t launch512(const K1WParams &p, int grid, cudaStream_t stream, int *occ_out) {
+    constexpr int WARPS = 4;
+    auto kern = k1w_512_kernel<OUT, WIN, WARPS, 3>;
+    constexpr size_t smem = sizeof(float2) * WARPS * K512_EX_F2;
+    if (occ_out) {
+        int nb = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, WARPS * 32, smem);
+        *occ_out = nb * WARPS;
+        return e;
+    }
+    kern<<<grid, WARPS * 32, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t k1w512_launch(const K1WParams &p, int output, bool win, int grid, cudaStream_t stream, int *occ_out) {
+    switch (output * 2 + (win ? 1 : 0)) {
+        case 0: return launch512<OUT_COMPLEX, false>(p, grid, stream, occ_out);
+        case 1: return launch512<OUT_COMPLEX, true>(p, grid, stream, occ_out);
+        case 2: return launch512<OUT_MAG, false>(p, grid, stream, occ_out);
+        case 3: return launch512<OUT_MAG, true>(p, grid, stream, occ_out);
+        case 4: return launch512<OUT_POWER, false>(p, grid, stream, occ_out);
+        case 5: return launch512<OUT_POWER, true>(p, grid, stream, occ_out);
+        case 6: return launch512<OUT_DB, false>(p, grid, stream, occ_out);
+        case 7: return launch512<OUT_DB, true>(p, grid, stream, occ_out);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -15,4 +15,9 @@ constexpr int K1W256_TABLE_F4 = 64 + 56 + 8;
 void k1w256_build_tables(const float *half_window, float4 *out /* K1W256_TABLE_F4 */);
 cudaError_t k1w256_launch(const K1WParams &p, int output, bool win, int grid, cudaStream_t stream, int *occ_out);
 
+// 512-point kernel, sixteen lanes per frame (fft_warp512.cuh): 4 warps per CTA, 2 frames per warp
+constexpr int K1W512_TABLE_F4 = (256 + 240 + 16) / 2;
+void k1w512_build_tables(const float *half_window, float4 *out /* K1W512_TABLE_F4 */);
+cudaError_t k1w512_launch(const K1WParams &p, int output, bool win, int grid, cudaStream_t stream, int *occ_out);
+
 }  // namespace kopek

@@ -266,6 +266,10 @@ static kopek_status upload_window(kopek_plan *p, const float *w) {
         std::vector<float4> t(K1W256_TABLE_F4);
         k1w256_build_tables(half.data(), t.data());
         KOPEK_CUDA(cudaMemcpy(p->d_k1w, t.data(), sizeof(float4) * K1W256_TABLE_F4, cudaMemcpyHostToDevice));
+    } else if (p->d_k1w && p->n == 512) {
+        std::vector<float4> t(K1W512_TABLE_F4);
+        k1w512_build_tables(half.data(), t.data());
+        KOPEK_CUDA(cudaMemcpy(p->d_k1w, t.data(), sizeof(float4) * K1W512_TABLE_F4, cudaMemcpyHostToDevice));
     }
     return KOPEK_OK;
 }
@@ -462,22 +466,24 @@ kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint
                 }
             }
         }
-        if (n == 256 && output <= KOPEK_OUT_DB) {
-            // configs[2] size: eight-lanes-per-frame kernel (fft_warp256.cuh); K1 stays for FULL bins / odd hops
+        if ((n == 256 || n == 512) && output <= KOPEK_OUT_DB) {
+            // sub-warp frames: 8 (fft_warp256.cuh) / 16 (fft_warp512.cuh) lanes per frame; K1 stays for FULL bins / odd hops
             const char *env = getenv("KOPEK_K1W_VARIANT");
             if (!(env && atoi(env) < 0)) {
-                std::vector<float4> t(K1W256_TABLE_F4);
-                k1w256_build_tables(nullptr, t.data());
-                if ((e = cudaMalloc(&p->d_k1w, sizeof(float4) * K1W256_TABLE_F4)) != cudaSuccess ||
-                    (e = cudaMemcpy(p->d_k1w, t.data(), sizeof(float4) * K1W256_TABLE_F4, cudaMemcpyHostToDevice)) !=
-                        cudaSuccess) {
-                    st = fail(KOPEK_ERR_CUDA, "K1W-256 table upload failed: %s", cudaGetErrorString(e));
+                const int nf4 = n == 256 ? K1W256_TABLE_F4 : K1W512_TABLE_F4;
+                std::vector<float4> t(nf4);
+                if (n == 256) k1w256_build_tables(nullptr, t.data());
+                else k1w512_build_tables(nullptr, t.data());
+                if ((e = cudaMalloc(&p->d_k1w, sizeof(float4) * nf4)) != cudaSuccess ||
+                    (e = cudaMemcpy(p->d_k1w, t.data(), sizeof(float4) * nf4, cudaMemcpyHostToDevice)) != cudaSuccess) {
+                    st = fail(KOPEK_ERR_CUDA, "K1W-%u table upload failed: %s", n, cudaGetErrorString(e));
                     break;
                 }
                 K1WParams dummy{};
-                e = k1w256_launch(dummy, (int)output, window != KOPEK_WINDOW_RECT, 0, nullptr, &p->k1w_warps_per_sm);
+                e = n == 256 ? k1w256_launch(dummy, (int)output, window != KOPEK_WINDOW_RECT, 0, nullptr, &p->k1w_warps_per_sm)
+                             : k1w512_launch(dummy, (int)output, window != KOPEK_WINDOW_RECT, 0, nullptr, &p->k1w_warps_per_sm);
                 if (e != cudaSuccess || p->k1w_warps_per_sm <= 0) {
-                    st = fail(KOPEK_ERR_CUDA, "K1W-256 kernel cannot be resident: %s", cudaGetErrorString(e));
+                    st = fail(KOPEK_ERR_CUDA, "K1W-%u kernel cannot be resident: %s", n, cudaGetErrorString(e));
                     break;
                 }
             }
@@ -548,7 +554,7 @@ static kopek_status stft_launch(const kopek_plan *plan, const float *d_samples, 
                                 cudaStream_t stream) {
     if (plan->output >= KOPEK_OUT_BANDS_LOG && (uintptr_t)d_samples % 16 != 0)
         return fail(KOPEK_ERR_INVALID, "band epilogues need a 16-byte aligned sample buffer");
-    if (plan->d_k1w && plan->n == 256 && plan->bins_mode == KOPEK_BINS_HALF && plan->hop % 4 == 0 &&
+    if (plan->d_k1w && (plan->n == 256 || plan->n == 512) && plan->bins_mode == KOPEK_BINS_HALF && plan->hop % 4 == 0 &&
         (uintptr_t)d_samples % 16 == 0) {
         K1WParams wp;
         wp.x = d_samples;
@@ -558,11 +564,14 @@ static kopek_status stft_launch(const kopek_plan *plan, const float *d_samples, 
         wp.hop = plan->hop;
         wp.pitch = plan->pitch;
         wp.band_scale = 1.0f;
-        const uint64_t groups = (frames + 3) / 4;                 // four frames per warp
+        const uint64_t fpw = plan->n == 256 ? 4 : 2;              // frames per warp
+        const uint64_t groups = (frames + fpw - 1) / fpw;
         const uint64_t warps = (uint64_t)plan->sm_count * plan->k1w_warps_per_sm;
         const int grid = (int)std::min<uint64_t>((groups + 3) / 4, warps / 4);
-        cudaError_t e = k1w256_launch(wp, (int)plan->output, plan->window != KOPEK_WINDOW_RECT, grid, stream, nullptr);
-        if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "K1W-256 launch failed: %s", cudaGetErrorString(e));
+        const bool win = plan->window != KOPEK_WINDOW_RECT;
+        cudaError_t e = plan->n == 256 ? k1w256_launch(wp, (int)plan->output, win, grid, stream, nullptr)
+                                       : k1w512_launch(wp, (int)plan->output, win, grid, stream, nullptr);
+        if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "K1W-%u launch failed: %s", plan->n, cudaGetErrorString(e));
         return KOPEK_OK;
     }
     if (plan->d_k1w && plan->n == 1024 && plan->bins_mode == KOPEK_BINS_HALF && plan->hop % 4 == 0 &&
