@@ -294,7 +294,7 @@ def run_ours(args):
                        "parallelism": f"frame-sharded x{world}, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": _ncu_traffic(), "peak_source": peak_src,
-                         "kernel": "k1w_1024_kernel<MAG,WIN> (warp per frame, TMA prefetch)", "kernel_ms": kernel_ms,
+                         "kernel": "k1w_1024b_kernel<MAG,WIN> (warp per frame, two shared-memory exchanges, LDG register prefetch)", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": frames * ALGO_BYTES_PER_FRAME,
                          "sustained": None if sustained is None else dict(
                              sustained, frac=frames * ALGO_BYTES_PER_FRAME / (sustained["ms_per_step"] * 1e-3) / 1e9 / peak)},

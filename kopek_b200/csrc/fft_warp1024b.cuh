@@ -1,0 +1,162 @@
+// K1W-1024b -- 1024-point real-input FFT + fused window / magnitude epilogue in TWO shared-memory exchanges (sm_100a).
+//
+// The three-pass kernel (fft_warp1024.cuh) needs 164 exchange wavefronts per frame on the LSU data pipe, the
+// pipe that bounds it (ncu: 83 % busy).  The 256- and 512-point kernels reach 95-99 % of the HBM roofline with a
+// two-pass 16-lane/8-lane layout; this kernel carries that structure to one warp per 1024-point frame:
+//
+//   M = 512 = 16 x 32,  n = 32 n1 + n0,  k = k1 + 16 k0
+//   A: lane l = n0 loads z[32 n1 + l] (n1 = 0..15), radix-16 over n1, multiplies by W512^{l k1}, publishes (k1, n0)
+//   B: the 32-point transform over n0 of butterfly k1 is shared by the lane PAIR (k1 = l/2, par = l%2): each lane
+//      gathers the 16 n0 of its parity and runs a radix-16 (even lane: E[j], odd lane: O[j]); the final radix-2,
+//      X[j] = E[j] + W32^j O[j], X[j+16] = E[j] - W32^j O[j], needs only HALF of the partner's values: one
+//      shfl.xor per word exchanges E[8..15] against O[0..7].  Lanes with n0 = 3 (mod 4) publish their pass-A
+//      outputs negated, which rotates the odd lane's radix-16 output by 8, so both lanes send register [8 + k]
+//      and no select is needed on the sending side.
+//   split: the partner Z[M-k] of bin k = k1 + 16 k0 lives in lane pair 16 - k1, other parity; each lane keeps
+//      eight bins k0 < 16 and publishes eight bins k0 >= 16.
+// Shared-memory wavefronts per frame: 32 + 32 (exchange) + 16 (shuffles) + 16 + 16 (split) = 112 instead of 164;
+// element (k1, n0) sits at 64-bit position 34 k1 + n0, which makes every access conflict free.
+// tools/k1w1024v2_model.py is the numpy model of these address functions.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fft_warp512.cuh"
+
+namespace kopek {
+
+constexpr int K1B_WIN_F2 = 512;            // (0.5 w[2i], 0.5 w[2i+1])
+constexpr int K1B_TW_F2 = 15 * 32;         // [k1-1][l]  +-W512^{l k1}  (negated for l = 3 mod 4)
+constexpr int K1B_CW_F2 = 8 * 2;           // [k][par]   W32^{k + 8 par}
+constexpr int K1B_PW_F2 = 32;              // [l]        -i W1024^{(l/2) + 128 (l%2)}
+constexpr int K1B_TABLE_F2 = K1B_WIN_F2 + K1B_TW_F2 + K1B_CW_F2 + K1B_PW_F2;
+constexpr int K1B_EX_F2 = 16 * 34;         // exchange positions per warp (4352 bytes)
+constexpr int K1B_STAGE_F2 = 260;          // bulk-store epilogue: the frame's 513 f32 (+ pad to 16 bytes) per warp
+
+__device__ __forceinline__ uint32_t k1b_smem_u32(const void *ptr) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(ptr));
+}
+
+// BULK (f32 outputs, rows 16-byte aligned: pitch % 4 == 0): the 513 values of a frame are staged in shared memory
+// and leave as ONE cp.async.bulk store of 2048 bytes (+ bin 512) -- the form that reaches link bandwidth when
+// p.out is a peer GPU's memory (kopek_plan_set_bulk_store).
+template <int OUT, bool WIN, int WARPS, int MINB, bool BULK = false>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+k1w_1024b_kernel(const K1WParams p) {
+    constexpr int M = 512;
+    static_assert(!BULK || (OUT == OUT_MAG || OUT == OUT_POWER || OUT == OUT_DB), "bulk store: f32 spectra only");
+    constexpr int WARP_F2 = K1B_EX_F2 + (BULK ? K1B_STAGE_F2 : 0);
+    extern __shared__ __align__(16) unsigned char k1b_smem[];
+    const int l = threadIdx.x & 31, k1 = l >> 1, par = l & 1;
+    float2 *ex = reinterpret_cast<float2 *>(k1b_smem) + (threadIdx.x >> 5) * WARP_F2;
+    float *stage = reinterpret_cast<float *>(ex + K1B_EX_F2);
+    float2 *exA = ex + l;                                   // + 34 k1'
+    const float2 *exB = ex + 34 * k1 + par;                 // + 2 m
+    float2 *zW = ex + l;                                    // + 32 i   (upper set, index i)
+    // partner of bin k1 + 16 k0 (k0 = 8 par + i): lane pair 16 - k1, other parity, upper index 7 - i;
+    // k1 = 0: the other lane of the same pair, upper index 8 - i (one row further; i = 0 handled from registers)
+    const float2 *zR = ex + (k1 ? 2 * (16 - k1) + (1 - par) : (l ^ 1) + 32);   // + 32 (7 - i)
+
+    const float2 *tab = reinterpret_cast<const float2 *>(p.tables);
+    float2 rw[16], rp[16], rc[8];
+    if constexpr (WIN) {
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) rw[n1] = tab[32 * n1 + l];
+    }
+#pragma unroll
+    for (int k = 1; k < 16; ++k) rp[k] = tab[K1B_WIN_F2 + 32 * (k - 1) + l];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) rc[k] = tab[K1B_WIN_F2 + K1B_TW_F2 + 2 * k + par];
+    const float2 pw_lane = tab[K1B_WIN_F2 + K1B_TW_F2 + K1B_CW_F2 + l];
+    const float sgn0 = (l & 3) == 3 ? -1.0f : 1.0f;         // sign of the untwiddled k1' = 0 output
+
+    const uint64_t total_warps = (uint64_t)gridDim.x * WARPS;
+    const uint64_t first = (uint64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+    auto load_frame = [&](uint64_t fr, float2 *dst) {
+        const float2 *xf = reinterpret_cast<const float2 *>(p.x + fr * p.hop) + l;
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) dst[n1] = __ldg(xf + 32 * n1);
+    };
+    float2 vn[16];
+    if (first < p.n_frames) load_frame(first, vn);
+
+    for (uint64_t frame = first; frame < p.n_frames; frame += total_warps) {
+        float2 e[16];
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) {
+            if constexpr (WIN) e[n1] = make_float2(vn[n1].x * rw[n1].x, vn[n1].y * rw[n1].y);
+            else e[n1] = vn[n1];
+        }
+        if (frame + total_warps < p.n_frames) load_frame(frame + total_warps, vn);
+
+        // ---- A: radix-16 over n1, twiddle (sign folded in), publish (k1', n0 = l)
+        Dft<16>::run(e);
+        exA[0] = make_float2(e[0].x * sgn0, e[0].y * sgn0);
+#pragma unroll
+        for (int k = 1; k < 16; ++k) exA[34 * k] = cmul(e[k], rp[k]);
+        __syncwarp();
+        // ---- B: gather the 16 n0 of this lane's parity, radix-16, then the radix-2 across the lane pair
+#pragma unroll
+        for (int m = 0; m < 16; ++m) e[m] = exB[2 * m];
+        Dft<16>::run(e);                                    // even lane: E[j]; odd lane: O[(j + 8) mod 16]
+        float2 zl[8], zu[8];                                // bins k0 = 8 par + i  /  16 + 8 par + i
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float2 recv;
+            recv.x = __shfl_xor_sync(0xffffffffu, e[8 + k].x, 1);
+            recv.y = __shfl_xor_sync(0xffffffffu, e[8 + k].y, 1);
+            // even lane: own = E[k], recv = O[k];  odd lane: own = O[8 + k], recv = E[8 + k]
+            const float2 E = par ? recv : e[k];
+            const float2 O = par ? e[k] : recv;
+            const float2 T = cmul(O, rc[k]);                // W32^{k + 8 par} O
+            zl[k] = E + T;
+            zu[k] = E - T;
+        }
+        __syncwarp();
+        // ---- split: publish the upper set, finish the pairs (k, M - k) of the lower set
+#pragma unroll
+        for (int i = 0; i < 8; ++i) zW[32 * i] = zu[i];
+        __syncwarp();
+        float2 b[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) b[i] = zR[32 * (7 - i)];
+        if (k1 == 0) b[0] = par ? zu[0] : zl[0];            // k = 128 pairs with Z[384] (own upper 0); k = 0 with itself
+        constexpr int EB = OUT == OUT_COMPLEX ? 8 : 4;
+        char *o_lo = reinterpret_cast<char *>(p.out) + (frame * p.pitch + (k1 + 128 * par)) * EB;
+        char *o_hi = reinterpret_cast<char *>(p.out) + (frame * p.pitch + (M - k1 - 128 * par)) * EB;
+        if constexpr (BULK) {
+            // the staging buffer is the warp's own and is never touched by the exchanges of the next frame
+            if (l == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous frame has left
+            __syncwarp();
+            o_lo = reinterpret_cast<char *>(stage + (k1 + 128 * par));
+            o_hi = reinterpret_cast<char *>(stage + (M - k1 - 128 * par));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float2 A = zl[i], B = b[i];
+            float2 S = make_float2(A.x + B.x, A.y - B.y);
+            float2 D = make_float2(A.x - B.x, A.y + B.y);
+            float2 Q = cmul(mul_w64(D, i), pw_lane);        // -i W1024^{k1 + 128 par + 16 i}
+            emit_at<OUT, WIN>(o_lo + 16 * i * EB, S + Q);
+            emit_at<OUT, WIN>(o_hi - 16 * i * EB, make_float2(S.x - Q.x, Q.y - S.y));
+        }
+        if (l == 0) emit_at<OUT, WIN>(o_lo + (M / 2) * EB, make_float2(2.0f * zu[0].x, -2.0f * zu[0].y));   // bin 256
+        if constexpr (BULK) {
+            __syncwarp();
+            if (l == 0) {
+                float *row = reinterpret_cast<float *>(p.out) + frame * p.pitch;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 2048;" ::"l"(row),
+                             "r"(k1b_smem_u32(stage)) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                row[M] = stage[M];                             // bin 512: the 513th value of the row
+            }
+        }
+        __syncwarp();
+    }
+    if constexpr (BULK) {
+        if (l == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+
+}  // namespace kopek

@@ -10,6 +10,12 @@ int k1w_variant_warps(int variant);
 cudaError_t k1w_launch(const K1WParams &p, int output, bool win, int variant, int grid, cudaStream_t stream,
                        int *occ_out);
 
+// 1024-point two-exchange kernel (fft_warp1024b.cuh): 4 warps per CTA, one frame per warp
+constexpr int K1B_TABLE_F4 = (512 + 480 + 16 + 32) / 2;
+void k1b_build_tables(const float *half_window, float4 *out /* K1B_TABLE_F4 */);
+cudaError_t k1b_launch(const K1WParams &p, int output, bool win, bool bulk, int grid, cudaStream_t stream,
+                       int *occ_out);
+
 // 256-point kernel, eight lanes per frame (fft_warp256.cuh): 4 warps per CTA, 4 frames per warp
 constexpr int K1W256_TABLE_F4 = 64 + 56 + 8;
 void k1w256_build_tables(const float *half_window, float4 *out /* K1W256_TABLE_F4 */);

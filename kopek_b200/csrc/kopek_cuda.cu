@@ -230,7 +230,9 @@ struct kopek_plan {
     k1_launch_fn launch;
     float *d_win;      // 0.5 * w
     float2 *d_tw, *d_pw;
-    float4 *d_k1w;     // tables of the warp-per-frame kernel (n == 1024 only)
+    float4 *d_k1w;     // tables of the warp-per-frame kernels (n == 256 / 512 / 1024)
+    float4 *d_k1b;     // tables of the two-exchange 1024-point kernel
+    int k1b_warps_per_sm;
     int k1w_variant, k1w_warps_per_sm;
     float band_scale;
     int bulk_store;
@@ -262,6 +264,11 @@ static kopek_status upload_window(kopek_plan *p, const float *w) {
         std::vector<float4> t(K1W_TABLE_F4);
         k1w_build_tables(half.data(), t.data());
         KOPEK_CUDA(cudaMemcpy(p->d_k1w, t.data(), sizeof(float4) * K1W_TABLE_F4, cudaMemcpyHostToDevice));
+        if (p->d_k1b) {
+            std::vector<float4> tb(K1B_TABLE_F4);
+            k1b_build_tables(half.data(), tb.data());
+            KOPEK_CUDA(cudaMemcpy(p->d_k1b, tb.data(), sizeof(float4) * K1B_TABLE_F4, cudaMemcpyHostToDevice));
+        }
     } else if (p->d_k1w && p->n == 256) {
         std::vector<float4> t(K1W256_TABLE_F4);
         k1w256_build_tables(half.data(), t.data());
@@ -279,6 +286,7 @@ static void plan_free_device(kopek_plan *p) {
     if (p->d_tw) cudaFree(p->d_tw);
     if (p->d_pw) cudaFree(p->d_pw);
     if (p->d_k1w) cudaFree(p->d_k1w);
+    if (p->d_k1b) cudaFree(p->d_k1b);
     for (HostSlot &s : p->slots) {
         if (s.d_in) cudaFree(s.d_in);
         if (s.d_out) cudaFree(s.d_out);
@@ -406,6 +414,7 @@ kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint
     p->bins = nb; p->pitch = out_pitch_elems; p->elem_bytes = output == KOPEK_OUT_COMPLEX ? 8 : 4;
     p->device = device; p->launch = launch; p->info = info();
     p->d_win = nullptr; p->d_tw = nullptr; p->d_pw = nullptr; p->last_launches = 0; p->slot_frames = 0;
+    p->d_k1b = nullptr; p->k1b_warps_per_sm = 0;
     p->d_k1w = nullptr; p->k1w_variant = 0; p->k1w_warps_per_sm = 0; p->band_scale = 1.0f; p->bulk_store = 0;
 
     kopek_status st = KOPEK_OK;
@@ -446,7 +455,8 @@ kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint
         if (n == 1024) {
             // headline size: warp-per-frame kernel (fft_warp1024.cuh); K1 stays for FULL bins / odd hops
             const char *env = getenv("KOPEK_K1W_VARIANT");
-            p->k1w_variant = env ? atoi(env) : 0;
+            p->k1w_variant = env ? atoi(env) : 200;      // 200 = the two-exchange kernel; 0..13 / <0: tuning only
+            const int setup_variant = p->k1w_variant == 200 ? 0 : p->k1w_variant;
             if (p->k1w_variant >= 0 || bands) {
                 if (p->k1w_variant < 0) p->k1w_variant = 0;
                 std::vector<float4> t(K1W_TABLE_F4);
@@ -458,11 +468,23 @@ kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint
                     break;
                 }
                 K1WParams dummy{};
-                e = k1w_launch(dummy, (int)output, window != KOPEK_WINDOW_RECT, p->k1w_variant, 0, nullptr,
+                e = k1w_launch(dummy, (int)output, window != KOPEK_WINDOW_RECT, setup_variant, 0, nullptr,
                                &p->k1w_warps_per_sm);
                 if (e != cudaSuccess || p->k1w_warps_per_sm <= 0) {
                     st = fail(KOPEK_ERR_CUDA, "K1W kernel cannot be resident: %s", cudaGetErrorString(e));
                     break;
+                }
+                if (output <= KOPEK_OUT_DB) {       // two-exchange kernel (fft_warp1024b.cuh) for the spectrum outputs
+                    std::vector<float4> tb(K1B_TABLE_F4);
+                    k1b_build_tables(nullptr, tb.data());
+                    if ((e = cudaMalloc(&p->d_k1b, sizeof(float4) * K1B_TABLE_F4)) != cudaSuccess ||
+                        (e = cudaMemcpy(p->d_k1b, tb.data(), sizeof(float4) * K1B_TABLE_F4, cudaMemcpyHostToDevice)) !=
+                            cudaSuccess ||
+                        (e = k1b_launch(dummy, (int)output, window != KOPEK_WINDOW_RECT, false, 0, nullptr,
+                                        &p->k1b_warps_per_sm)) != cudaSuccess) {
+                        st = fail(KOPEK_ERR_CUDA, "K1W-1024b setup failed: %s", cudaGetErrorString(e));
+                        break;
+                    }
                 }
             }
         }
@@ -587,7 +609,16 @@ static kopek_status stft_launch(const kopek_plan *plan, const float *d_samples, 
         // bulk-store epilogue: opt-in, f32 spectra, 16-byte aligned rows (else the direct 32-bit stores)
         const bool bulk = plan->bulk_store && plan->output >= KOPEK_OUT_MAG && plan->output <= KOPEK_OUT_DB &&
                           plan->pitch % 4 == 0 && (uintptr_t)d_out % 16 == 0;
-        const int variant = bulk ? 100 : plan->k1w_variant;
+        const int variant = bulk ? 100 : plan->k1w_variant == 200 ? 0 : plan->k1w_variant;
+        if (plan->d_k1b && plan->k1w_variant == 200) {
+            wp.tables = plan->d_k1b;
+            const uint64_t warps_b = (uint64_t)plan->sm_count * plan->k1b_warps_per_sm;
+            const int grid_b = (int)std::min<uint64_t>((frames + 3) / 4, warps_b / 4);
+            cudaError_t eb = k1b_launch(wp, (int)plan->output, plan->window != KOPEK_WINDOW_RECT, bulk, grid_b, stream,
+                                        nullptr);
+            if (eb != cudaSuccess) return fail(KOPEK_ERR_CUDA, "K1W-1024b launch failed: %s", cudaGetErrorString(eb));
+            return KOPEK_OK;
+        }
         const uint64_t warps = (uint64_t)plan->sm_count * plan->k1w_warps_per_sm;
         const int wpb = k1w_variant_warps(variant);
         const int grid = (int)std::min<uint64_t>((frames + wpb - 1) / wpb, warps / wpb);
