@@ -11,6 +11,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libkopek_cuda.so")
+if os.environ.get("KOPEK_TUNE_TAG"):      # tuning builds of the same library (tools/tune.py), never a different backend
+    LIB_PATH = os.path.join(_HERE, "lib", "tune", os.environ["KOPEK_TUNE_TAG"], "libkopek_cuda.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED = 0, -1, -2, -3, -4
 WINDOW_RECT, WINDOW_HANN, WINDOW_HAMMING, WINDOW_CUSTOM = 0, 1, 2, 3

@@ -58,12 +58,18 @@ def _run(cmd, verbose):
         print(r.stdout + r.stderr, flush=True)
 
 
-def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False, tag: str = "", defs=()) -> str:
+    """tag / defs: tuning builds only (tools/): extra -D flags, objects and library under lib/tune/<tag>/."""
+    global OBJ, LIB
+    if tag:
+        OBJ = os.path.join(HERE, "lib", "tune", tag, "obj")
+        LIB = os.path.join(HERE, "lib", "tune", tag, "libkopek_cuda.so")
     if not force and not _stale(LIB):
         return LIB
     os.makedirs(OBJ, exist_ok=True)
     cc = nvcc()
     extra = ["-Xptxas", "-v"] if ptxas_info else []
+    extra += list(defs)
     if os.environ.get("KOPEK_K1_PREF") is not None:   # tuning: force the K1 register prefetch on/off for every size
         extra.append("-DK1_PREF_ALL=" + ("true" if os.environ["KOPEK_K1_PREF"] == "1" else "false"))
     if os.environ.get("KOPEK_K1W_SWEEP"):      # build every K1W tuning variant (tools/sweep_k1w.py)
@@ -73,7 +79,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
         obj = os.path.join(OBJ, f"k1_{n}.o")
         jobs.append((obj, [cc, *ARCH, *COMMON, *extra, f"-DKOPEK_K1_N={n}", "-c", os.path.join(CSRC, "k1_inst.cu"),
                            "-o", obj]))
-    for name in ("kopek_cuda", "k1w_inst", "fft_large", "synth"):
+    for name in ("kopek_cuda", "k1w_inst", "k1m_inst", "fft_large", "synth"):
         src = os.path.join(CSRC, name + ".cu")
         if os.path.exists(src):
             obj = os.path.join(OBJ, name + ".o")

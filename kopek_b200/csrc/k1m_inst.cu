@@ -1,0 +1,125 @@
+// K1M instantiations (fft_team.cuh): team-per-frame kernels for N = 2048 (R = 4) and 4096 (R = 8); R = 2 (N = 1024)
+// is built for testing only (KOPEK_K1W_VARIANT=300).
+#include <cmath>
+
+#include "k1w_launch.cuh"
+#include "fft_team.cuh"
+
+namespace kopek {
+
+template <int R> static void build_tables_r(const float *half_window, double cs_a, double cs_b, float2 *out) {
+    using G = K1MGeom<R>;
+    constexpr int T = G::T, QD = G::QD;
+    const double tau = 2.0 * M_PI;
+    for (int i = 0; i < G::WIN_F2; ++i)
+        out[i] = half_window ? make_float2(half_window[2 * i], half_window[2 * i + 1]) : make_float2(0.5f, 0.5f);
+    float2 *rp = out + G::WIN_F2;
+    for (int k1 = 0; k1 < 16; ++k1)
+        for (int t = 0; t < T; ++t) {
+            // W_M^{t k1} W_R^{(t % R)(t / R)}: both exponents reduced exactly before the division
+            const int a = (t * k1) % G::M, b = ((t % R) * (t / R)) % R;
+            const double x = -tau * ((double)a / G::M + (double)b / R);
+            rp[k1 * T + t] = make_float2((float)cos(x), (float)sin(x));
+        }
+    float2 *tw = rp + G::RP_F2;
+    for (int x = 0; x < R; ++x)
+        for (int d = 0; d < QD; ++d)
+            for (int t = 0; t < T; ++t) {
+                const int r = t % R, rs = (r + x) % R, j = QD * r + d;
+                const double a = -tau * (double)((rs * j) % T) / T;
+                tw[(x * QD + d) * T + t] = make_float2((float)cos(a), (float)sin(a));
+            }
+    float2 *ph = tw + G::TW_F2;
+    for (int q = 1; q <= R / 2; ++q)
+        for (int t = 0; t < T; ++t) {
+            const double a = -tau * (double)(((t % R) * q) % R) / R;
+            ph[(q - 1) * T + t] = make_float2((float)cos(a), (float)sin(a));
+        }
+    float2 *pw = ph + G::PH_F2;
+    for (int t = 0; t < T; ++t) {
+        const double a = tau * (double)t / G::N;
+        pw[t] = make_float2((float)-sin(a), (float)-cos(a));
+    }
+    // cosine-sum window w[n] = a - b cos(2 pi n / N), halved like the table: lane constants at n = 2 t + c
+    float2 *cs = pw + G::PW_F2;
+    for (int t = 0; t < T; ++t) {
+        for (int c = 0; c < 2; ++c) {
+            const double th = tau * (double)(2 * t + c) / G::N;
+            cs[c * T + t] = make_float2((float)(-0.5 * cs_b * cos(th)), (float)(0.5 * cs_b * sin(th)));
+        }
+        cs[2 * T + t] = make_float2((float)(0.5 * cs_a), 0.0f);
+        cs[3 * T + t] = out[t];                  // the frame edges keep their table values (n1 = 0, n1 = 15)
+        cs[4 * T + t] = out[15 * T + t];
+    }
+}
+
+int k1m_table_f4(int n) {
+    switch (n) {
+        case 1024: return K1MGeom<2>::TABLE_F2 / 2;
+        case 2048: return K1MGeom<4>::TABLE_F2 / 2;
+        case 4096: return K1MGeom<8>::TABLE_F2 / 2;
+        default: return 0;
+    }
+}
+
+void k1m_build_tables(int n, const float *half_window, double cs_a, double cs_b, float4 *out) {
+    float2 *o = reinterpret_cast<float2 *>(out);
+    if (n == 1024) build_tables_r<2>(half_window, cs_a, cs_b, o);
+    else if (n == 2048) build_tables_r<4>(half_window, cs_a, cs_b, o);
+    else build_tables_r<8>(half_window, cs_a, cs_b, o);
+}
+
+#ifndef KOPEK_K1M_PF
+#define KOPEK_K1M_PF 0      // L2 prefetch distance in frames per team: measured 0/2/3/5 -> no gain (not latency bound on HBM)
+#endif
+// resident teams per SM the register allocation is held to: 12 warps per SM (168 registers) for the rectangular and
+// cosine-sum windows -- measured 76 -> 86 % (N = 2048) and 70 -> 80 % (N = 4096) against 8 warps -- and 8 warps for
+// the table window, whose 32 extra registers would otherwise spill
+template <int R, int WINK> struct K1MOcc {
+    static constexpr int MINB = R == 8 ? (WINK == 1 ? 2 : 3) : R == 4 ? (WINK == 1 ? 4 : 6) : 12;
+};
+
+template <int R, int OUT, int WIN>
+static cudaError_t launch_m(const K1WParams &p, int grid, cudaStream_t stream, int *occ_out) {
+    auto kern = k1m_kernel<R, OUT, WIN, K1MOcc<R, WIN>::MINB, KOPEK_K1M_PF>;
+    constexpr size_t smem = K1MGeom<R>::SMEM;
+    if (occ_out) {
+        int nb = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 16 * R, smem);
+        *occ_out = nb;                                       // teams (CTAs) per SM
+        return e;
+    }
+    kern<<<grid, 16 * R, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+template <int R>
+static cudaError_t launch_r(const K1WParams &p, int output, int wink, int grid, cudaStream_t stream, int *occ_out) {
+    switch (output * 3 + wink) {
+        case 0: return launch_m<R, OUT_COMPLEX, 0>(p, grid, stream, occ_out);
+        case 1: return launch_m<R, OUT_COMPLEX, 1>(p, grid, stream, occ_out);
+        case 2: return launch_m<R, OUT_COMPLEX, 2>(p, grid, stream, occ_out);
+        case 3: return launch_m<R, OUT_MAG, 0>(p, grid, stream, occ_out);
+        case 4: return launch_m<R, OUT_MAG, 1>(p, grid, stream, occ_out);
+        case 5: return launch_m<R, OUT_MAG, 2>(p, grid, stream, occ_out);
+        case 6: return launch_m<R, OUT_POWER, 0>(p, grid, stream, occ_out);
+        case 7: return launch_m<R, OUT_POWER, 1>(p, grid, stream, occ_out);
+        case 8: return launch_m<R, OUT_POWER, 2>(p, grid, stream, occ_out);
+        case 9: return launch_m<R, OUT_DB, 0>(p, grid, stream, occ_out);
+        case 10: return launch_m<R, OUT_DB, 1>(p, grid, stream, occ_out);
+        case 11: return launch_m<R, OUT_DB, 2>(p, grid, stream, occ_out);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t k1m_launch(int n, const K1WParams &p, int output, int wink, int grid, cudaStream_t stream, int *occ_out) {
+    if (wink < 0 || wink > 2) return cudaErrorInvalidValue;
+    switch (n) {
+        case 1024: return launch_r<2>(p, output, wink, grid, stream, occ_out);
+        case 2048: return launch_r<4>(p, output, wink, grid, stream, occ_out);
+        case 4096: return launch_r<8>(p, output, wink, grid, stream, occ_out);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace kopek

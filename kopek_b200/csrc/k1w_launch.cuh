@@ -26,4 +26,11 @@ constexpr int K1W512_TABLE_F4 = (256 + 240 + 16) / 2;
 void k1w512_build_tables(const float *half_window, float4 *out /* K1W512_TABLE_F4 */);
 cudaError_t k1w512_launch(const K1WParams &p, int output, bool win, int grid, cudaStream_t stream, int *occ_out);
 
+// team-per-frame kernels (fft_team.cuh): n = 2048 (64 lanes) / 4096 (128 lanes); n = 1024 (32 lanes) for testing
+int k1m_table_f4(int n);
+// wink: 0 rectangular, 1 window table (half_window), 2 cosine-sum window w[n] = cs_a - cs_b cos(2 pi n / n) on the fly
+void k1m_build_tables(int n, const float *half_window, double cs_a, double cs_b, float4 *out /* k1m_table_f4(n) */);
+cudaError_t k1m_launch(int n, const K1WParams &p, int output, int wink, int grid, cudaStream_t stream,
+                       int *occ_out /* teams per SM */);
+
 }  // namespace kopek

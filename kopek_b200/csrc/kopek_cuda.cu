@@ -233,6 +233,8 @@ struct kopek_plan {
     float4 *d_k1w;     // tables of the warp-per-frame kernels (n == 256 / 512 / 1024)
     float4 *d_k1b;     // tables of the two-exchange 1024-point kernel
     int k1b_warps_per_sm;
+    float4 *d_k1m;     // tables of the team-per-frame kernel (n == 2048 / 4096; n == 1024 with KOPEK_K1W_VARIANT=300)
+    int k1m_teams_per_sm, k1m_wink;
     int k1w_variant, k1w_warps_per_sm;
     float band_scale;
     int bulk_store;
@@ -260,6 +262,12 @@ static kopek_status upload_window(kopek_plan *p, const float *w) {
     for (uint32_t i = 0; i < p->n; ++i) half[i] = 0.5f * w[i];
     if (!p->d_win) KOPEK_CUDA(cudaMalloc(&p->d_win, p->n * sizeof(float)));
     KOPEK_CUDA(cudaMemcpy(p->d_win, half.data(), p->n * sizeof(float), cudaMemcpyHostToDevice));
+    if (p->d_k1m) {
+        std::vector<float4> t(k1m_table_f4((int)p->n));
+        const double cs_a = p->window == KOPEK_WINDOW_HANN ? 0.5 : 0.54, cs_b = p->window == KOPEK_WINDOW_HANN ? 0.5 : 0.46;
+        k1m_build_tables((int)p->n, half.data(), cs_a, cs_b, t.data());
+        KOPEK_CUDA(cudaMemcpy(p->d_k1m, t.data(), sizeof(float4) * t.size(), cudaMemcpyHostToDevice));
+    }
     if (p->d_k1w && p->n == 1024) {
         std::vector<float4> t(K1W_TABLE_F4);
         k1w_build_tables(half.data(), t.data());
@@ -287,6 +295,7 @@ static void plan_free_device(kopek_plan *p) {
     if (p->d_pw) cudaFree(p->d_pw);
     if (p->d_k1w) cudaFree(p->d_k1w);
     if (p->d_k1b) cudaFree(p->d_k1b);
+    if (p->d_k1m) cudaFree(p->d_k1m);
     for (HostSlot &s : p->slots) {
         if (s.d_in) cudaFree(s.d_in);
         if (s.d_out) cudaFree(s.d_out);
@@ -414,7 +423,7 @@ kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint
     p->bins = nb; p->pitch = out_pitch_elems; p->elem_bytes = output == KOPEK_OUT_COMPLEX ? 8 : 4;
     p->device = device; p->launch = launch; p->info = info();
     p->d_win = nullptr; p->d_tw = nullptr; p->d_pw = nullptr; p->last_launches = 0; p->slot_frames = 0;
-    p->d_k1b = nullptr; p->k1b_warps_per_sm = 0;
+    p->d_k1b = nullptr; p->k1b_warps_per_sm = 0; p->d_k1m = nullptr; p->k1m_teams_per_sm = 0;
     p->d_k1w = nullptr; p->k1w_variant = 0; p->k1w_warps_per_sm = 0; p->band_scale = 1.0f; p->bulk_store = 0;
 
     kopek_status st = KOPEK_OK;
@@ -456,7 +465,7 @@ kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint
             // headline size: warp-per-frame kernel (fft_warp1024.cuh); K1 stays for FULL bins / odd hops
             const char *env = getenv("KOPEK_K1W_VARIANT");
             p->k1w_variant = env ? atoi(env) : 200;      // 200 = the two-exchange kernel; 0..13 / <0: tuning only
-            const int setup_variant = p->k1w_variant == 200 ? 0 : p->k1w_variant;
+            const int setup_variant = p->k1w_variant >= 200 ? 0 : p->k1w_variant;
             if (p->k1w_variant >= 0 || bands) {
                 if (p->k1w_variant < 0) p->k1w_variant = 0;
                 std::vector<float4> t(K1W_TABLE_F4);
@@ -508,6 +517,27 @@ kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint
                     st = fail(KOPEK_ERR_CUDA, "K1W-%u kernel cannot be resident: %s", n, cudaGetErrorString(e));
                     break;
                 }
+            }
+        }
+        {
+            // team-per-frame kernel (fft_team.cuh): 2048 / 4096 points; K1 stays for FULL bins / odd hops
+            const char *env = getenv("KOPEK_K1W_VARIANT");
+            const int v = env ? atoi(env) : 0;
+            if (output <= KOPEK_OUT_DB && ((v >= 0 && (n == 2048 || n == 4096)) || (v == 300 && n == 1024))) {
+                std::vector<float4> t(k1m_table_f4((int)n));
+                k1m_build_tables((int)n, nullptr, 0.0, 0.0, t.data());
+                K1WParams dummy{};
+                p->k1m_wink = window == KOPEK_WINDOW_RECT ? 0 : window == KOPEK_WINDOW_CUSTOM ? 1 : 2;
+                if (env && v == 301) p->k1m_wink = window == KOPEK_WINDOW_RECT ? 0 : 1;    // tuning: table window
+                if ((e = cudaMalloc(&p->d_k1m, sizeof(float4) * t.size())) != cudaSuccess ||
+                    (e = cudaMemcpy(p->d_k1m, t.data(), sizeof(float4) * t.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
+                    (e = k1m_launch((int)n, dummy, (int)output, p->k1m_wink, 0, nullptr,
+                                    &p->k1m_teams_per_sm)) != cudaSuccess ||
+                    p->k1m_teams_per_sm <= 0) {
+                    st = fail(KOPEK_ERR_CUDA, "K1M-%u setup failed: %s", n, cudaGetErrorString(e));
+                    break;
+                }
+                if (getenv("KOPEK_DEBUG")) fprintf(stderr, "[kopek] K1M-%u: %d teams per SM\n", n, p->k1m_teams_per_sm);
             }
         }
         if (window == KOPEK_WINDOW_HANN || window == KOPEK_WINDOW_HAMMING) {
@@ -596,6 +626,20 @@ static kopek_status stft_launch(const kopek_plan *plan, const float *d_samples, 
         if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "K1W-%u launch failed: %s", plan->n, cudaGetErrorString(e));
         return KOPEK_OK;
     }
+    if (plan->d_k1m && plan->bins_mode == KOPEK_BINS_HALF && plan->hop % 2 == 0 && (uintptr_t)d_samples % 8 == 0) {
+        K1WParams wp;
+        wp.x = d_samples;
+        wp.out = d_out;
+        wp.tables = plan->d_k1m;
+        wp.n_frames = frames;
+        wp.hop = plan->hop;
+        wp.pitch = plan->pitch;
+        wp.band_scale = 1.0f;
+        const int grid = (int)std::min<uint64_t>(frames, (uint64_t)plan->sm_count * plan->k1m_teams_per_sm);
+        cudaError_t e = k1m_launch((int)plan->n, wp, (int)plan->output, plan->k1m_wink, grid, stream, nullptr);
+        if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "K1M-%u launch failed: %s", plan->n, cudaGetErrorString(e));
+        return KOPEK_OK;
+    }
     if (plan->d_k1w && plan->n == 1024 && plan->bins_mode == KOPEK_BINS_HALF && plan->hop % 4 == 0 &&
         (uintptr_t)d_samples % 16 == 0) {
         K1WParams wp;
@@ -609,8 +653,8 @@ static kopek_status stft_launch(const kopek_plan *plan, const float *d_samples, 
         // bulk-store epilogue: opt-in, f32 spectra, 16-byte aligned rows (else the direct 32-bit stores)
         const bool bulk = plan->bulk_store && plan->output >= KOPEK_OUT_MAG && plan->output <= KOPEK_OUT_DB &&
                           plan->pitch % 4 == 0 && (uintptr_t)d_out % 16 == 0;
-        const int variant = bulk ? 100 : plan->k1w_variant == 200 ? 0 : plan->k1w_variant;
-        if (plan->d_k1b && plan->k1w_variant == 200) {
+        const int variant = bulk ? 100 : plan->k1w_variant >= 200 ? 0 : plan->k1w_variant;
+        if (plan->d_k1b && plan->k1w_variant >= 200) {
             wp.tables = plan->d_k1b;
             const uint64_t warps_b = (uint64_t)plan->sm_count * plan->k1b_warps_per_sm;
             const int grid_b = (int)std::min<uint64_t>((frames + 3) / 4, warps_b / 4);
