@@ -41,10 +41,20 @@ __host__ __device__ constexpr int k3_swz(int q) { return q ^ ((q >> 4) & 15); }
 // FIRST_MAP remaps the logical index of the very first read (pass 2: tile-major block order).
 // XTW (last stage of pass 1 only): the inter-step twiddle W_n^{n2 q} is applied to output q in registers just
 // before the final write (two-level table: W^m = W^{4096 (m >> 12)} W^{m & 4095}), saving a pass over the tile.
+struct K3NoOut {
+    static constexpr bool enabled = false;
+    __device__ __forceinline__ void reads_done() const {}
+    __device__ __forceinline__ void store(int, float2) const {}
+};
+
+// OUT (last stage only): instead of writing the result back to shared memory, `out.reads_done()` runs right after the
+// barrier that ends the stage's reads (the tile buffer is free from here on: the caller starts the TMA load of the
+// NEXT tile into it) and every output q goes straight to global memory through `out.store(q, v)`.
 template <int COLS, int RAD, int NS, int M, int T, bool READ_LINEAR, bool WRITE_LINEAR, bool TILE_MAJOR_IN,
-          bool XTW = false>
+          bool XTW = false, class OUT = K3NoOut>
 __device__ __forceinline__ void k3_stage(float2 *buf, const float2 *tw, int tid, int c, uint32_t n2 = 0,
-                                         const float2 *tw_hi = nullptr, const float2 *tw_lo = nullptr) {
+                                         const float2 *tw_hi = nullptr, const float2 *tw_lo = nullptr,
+                                         const OUT &out = OUT()) {
     constexpr int NB = 16 / RAD;
     float2 d[16];
 #pragma unroll
@@ -62,9 +72,13 @@ __device__ __forceinline__ void k3_stage(float2 *buf, const float2 *tw, int tid,
             d[i * RAD + t] = v;
         }
     }
+    if constexpr (OUT::enabled) {
+        __syncthreads();
+        out.reads_done();
+    }
 #pragma unroll
     for (int i = 0; i < NB; ++i) Dft<RAD>::run(d + i * RAD);
-    __syncthreads();
+    if constexpr (!OUT::enabled) __syncthreads();
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
         int j = tid + T * i;
@@ -88,26 +102,28 @@ __device__ __forceinline__ void k3_stage(float2 *buf, const float2 *tw, int tid,
 #pragma unroll
         for (int k = 0; k < RAD; ++k) {
             int q = base + k * NS;
-            buf[(WRITE_LINEAR ? q : k3_swz(q)) * COLS + c] = d[i * RAD + k];
+            if constexpr (OUT::enabled) out.store(q, d[i * RAD + k]);
+            else buf[(WRITE_LINEAR ? q : k3_swz(q)) * COLS + c] = d[i * RAD + k];
         }
     }
-    __syncthreads();
+    if constexpr (!OUT::enabled) __syncthreads();
 }
 
-// M-point FFT of the COLS interleaved columns in `buf`; result dense: buf[k * COLS + c].
-template <int COLS, int M, bool TILE_MAJOR_IN, bool XTW>
-__device__ __forceinline__ void k3_fft_tile(float2 *buf, const float2 *tw, int tid, int c, uint32_t n2 = 0,
-                                            const float2 *tw_hi = nullptr, const float2 *tw_lo = nullptr) {
+// M-point FFT of the COLS interleaved columns in `buf`; the last stage hands its outputs to `out` (global memory).
+template <int COLS, int M, bool TILE_MAJOR_IN, bool XTW, class OUT>
+__device__ __forceinline__ void k3_fft_tile(float2 *buf, const float2 *tw, int tid, int c, const OUT &out,
+                                            uint32_t n2 = 0, const float2 *tw_hi = nullptr,
+                                            const float2 *tw_lo = nullptr) {
     using C = K3Cfg<M>;
     constexpr int T = M / 16;
     if constexpr (C::R2 > 1) {
         k3_stage<COLS, C::R0, 1, M, T, true, false, TILE_MAJOR_IN>(buf, tw, tid, c);
         k3_stage<COLS, C::R1, C::R0, M, T, false, false, false>(buf, tw, tid, c);
-        k3_stage<COLS, C::R2, C::R0 * C::R1, M, T, false, true, false, XTW>(buf, tw + (C::R1 - 1) * C::R0, tid, c, n2,
-                                                                             tw_hi, tw_lo);
+        k3_stage<COLS, C::R2, C::R0 * C::R1, M, T, false, true, false, XTW, OUT>(buf, tw + (C::R1 - 1) * C::R0, tid, c,
+                                                                                  n2, tw_hi, tw_lo, out);
     } else {
         k3_stage<COLS, C::R0, 1, M, T, true, false, TILE_MAJOR_IN>(buf, tw, tid, c);
-        k3_stage<COLS, C::R1, C::R0, M, T, false, true, false, XTW>(buf, tw, tid, c, n2, tw_hi, tw_lo);
+        k3_stage<COLS, C::R1, C::R0, M, T, false, true, false, XTW, OUT>(buf, tw, tid, c, n2, tw_hi, tw_lo, out);
     }
 }
 
@@ -136,26 +152,44 @@ template <int N> __device__ __forceinline__ void tma_store_wait_read() {
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 
-// Both passes are PERSISTENT: one CTA per SM loops over its tiles.  The tile buffer is a ring of
-// 256-row boxes: each box is stored with its own bulk group, and as soon as the TMA engine has read
-// box b out of shared memory (wait_group.read) the same box of the NEXT tile is loaded into it, so the
-// store of tile i and the load of tile i+1 overlap (only the FFT itself is not overlapped with memory).
+// Both passes are PERSISTENT CTAs looping over their tiles.  A tile is loaded by TMA (pass 1: 2-D boxes of the
+// strided column tile; pass 2: 1-D bulk copies of one contiguous block), transformed in place in shared memory, and
+// the LAST stage stores its outputs from registers straight to global memory.  The tile buffer is therefore free as
+// soon as the last stage has read it: the load of the CTA's next tile is issued at that point and overlaps the last
+// butterflies, the inter-step twiddle and the stores (the first version wrote the result back to shared memory,
+// stored it with TMA and could only reload a box once that store had drained: 0.162 ms at 2^24).
+// tools/micro/tma_rows.cu measured the memory side alone on this matrix: TMA loads of 16 / 32 / 64-byte rows run at
+// 4.0 / 4.9 / 5.8 TB/s, TMA stores at 2.7 / 4.6 / 4.9 TB/s, plain 64-byte-run stores at 5.3 TB/s.
+
+// pass 1 output: thread (tid, c) holds A[k1][n2 = 2 s + c]; mid is tile-major [k1/4][n2/2][k1%4][n2%2], so the 16
+// lanes x 2 columns of a warp write four 64-byte segments per store instruction
+struct K3Out1 {
+    static constexpr bool enabled = true;
+    float2 *dst;               // mid + s * 8 + c
+    size_t seg_stride;         // (N2 / 2) * 8 complex between k1/4 blocks
+    uint64_t *bar;
+    const CUtensorMap *in_map;
+    float2 *buf;
+    int next_tile, n1;
+    __device__ __forceinline__ void reads_done() const {
+        if (threadIdx.x == 0 && next_tile >= 0) {
+            mbar_expect_tx(bar, n1 * 16);
+            for (int r0 = 0; r0 < n1; r0 += 256) tma_load_2d(buf + r0 * 2, in_map, 4 * next_tile, r0, bar);
+        }
+    }
+    __device__ __forceinline__ void store(int k1, float2 v) const { dst[(size_t)(k1 >> 2) * seg_stride + (k1 & 3) * 2] = v; }
+};
 
 // ---- pass 1: column tiles s (columns 2s, 2s+1), all n1.  Two-column tiles (N1 x 16 B = 64 KB at N1 = 4096)
-// let TWO CTAs share an SM, so one transforms while the other waits on shared memory or on its TMA
-// traffic (a single 128 KB tile per SM ran its 32 warps in lockstep between __syncthreads).  The two halves
-// of every 32-byte DRAM sector are fetched by neighbouring CTAs at about the same time and merge in L2.
+// let TWO CTAs share an SM, so one transforms while the other waits on shared memory or on its TMA traffic.
 template <int N1>
 __global__ void __launch_bounds__(N1 / 8, 2)
-k3_pass1(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap mid_map, K3Tables tb,
-         int n_tiles) {
+k3_pass1(const __grid_constant__ CUtensorMap in_map, float2 *__restrict__ mid, K3Tables tb, int n_tiles) {
     extern __shared__ __align__(128) unsigned char k3_smem[];
     float2 *buf = reinterpret_cast<float2 *>(k3_smem);                 // N1 x 2 complex, dense
     float2 *s_tw = reinterpret_cast<float2 *>(k3_smem + (size_t)N1 * 16);   // stage twiddles, N1 entries
     uint64_t *bar = reinterpret_cast<uint64_t *>(k3_smem + (size_t)N1 * 24);
     for (int i = threadIdx.x; i < N1; i += N1 / 8) s_tw[i] = tb.tw_sub1[i];
-    constexpr int NBOX = N1 >= 1024 ? N1 / 1024 : 1;                   // load/store granule: 1024 rows = 16 KB
-    constexpr int BOX_ROWS = N1 / NBOX;
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -171,50 +205,42 @@ k3_pass1(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUt
     for (int s = blockIdx.x; s < n_tiles; s += gridDim.x) {
         mbar_wait(bar, phase);
         phase ^= 1;
-        // sub-transform + inter-step twiddle W_n^{n2 k1}, n2 = 2s + c (fused into the last stage's write)
-        k3_fft_tile<2, N1, false, true>(buf, s_tw, tid, c, 2u * s + c, tb.tw_hi, tb.tw_lo);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic writes -> TMA store reads
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            // buf is [k1][c] dense = rows u = k1/4 of 8 complex (16 floats): the 64-byte segments of mid
-#pragma unroll
-            for (int b = 0; b < NBOX; ++b) {
-                for (int u0 = b * (BOX_ROWS / 4); u0 < (b + 1) * (BOX_ROWS / 4); u0 += 256)
-                    tma_store_2d(&mid_map, 16 * s, u0, buf + u0 * 8);
-                tma_store_commit();
-            }
-            const int nxt = s + gridDim.x;
-            if (nxt < n_tiles) mbar_expect_tx(bar, N1 * 16);
-#pragma unroll
-            for (int b = 0; b < NBOX; ++b) {
-                // box b has left shared memory once at most NBOX-1-b younger groups are still reading
-                switch (NBOX - 1 - b) {
-                    case 0: tma_store_wait_read<0>(); break;
-                    case 1: tma_store_wait_read<1>(); break;
-                    case 2: tma_store_wait_read<2>(); break;
-                    default: tma_store_wait_read<3>(); break;
-                }
-                if (nxt < n_tiles)
-                    for (int r0 = b * BOX_ROWS; r0 < (b + 1) * BOX_ROWS; r0 += 256)
-                        tma_load_2d(buf + r0 * 2, &in_map, 4 * nxt, r0, bar);
-            }
+        const int nxt = s + gridDim.x;
+        K3Out1 out{mid + (size_t)s * 8 + c, (size_t)n_tiles * 8, bar, &in_map, buf, nxt < n_tiles ? nxt : -1, N1};
+        // sub-transform + inter-step twiddle W_n^{n2 k1}, n2 = 2s + c (applied in registers before the stores)
+        k3_fft_tile<2, N1, false, true>(buf, s_tw, tid, c, out, 2u * s + c, tb.tw_hi, tb.tw_lo);
+    }
+}
+
+// pass 2 output: thread (tid, c) holds X[k1 + N1 k2], k1 = 4 u + c: the 8 lanes x 4 rows of a warp write eight
+// 32-byte runs per store instruction
+struct K3Out2 {
+    static constexpr bool enabled = true;
+    float2 *dst;               // out + 4 u + c
+    size_t n1;
+    uint64_t *bar;
+    const char *next_src;      // next tile's contiguous block of mid, or nullptr
+    unsigned char *smem;
+    int bytes, chunk;
+    __device__ __forceinline__ void reads_done() const {
+        if (threadIdx.x == 0 && next_src) {
+            mbar_expect_tx(bar, bytes);
+            for (int off = 0; off < bytes; off += chunk) tma_load_1d(smem + off, next_src + off, chunk, bar);
         }
     }
-    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
+    __device__ __forceinline__ void store(int k2, float2 v) const { dst[(size_t)k2 * n1] = v; }
+};
 
 // ---- pass 2: row tiles u (rows k1 = 4u..4u+3), all n2; block mid[u] is contiguous
 template <int N2>
 __global__ void __launch_bounds__(N2 / 4, 1)
-k3_pass2(const float2 *__restrict__ mid, const __grid_constant__ CUtensorMap out_map, K3Tables tb, int n_tiles) {
+k3_pass2(const float2 *__restrict__ mid, float2 *__restrict__ outp, K3Tables tb, int n_tiles) {
     extern __shared__ __align__(128) unsigned char k3_smem[];
     float2 *buf = reinterpret_cast<float2 *>(k3_smem);
     float2 *s_tw = reinterpret_cast<float2 *>(k3_smem + (size_t)N2 * 32);
     uint64_t *bar = reinterpret_cast<uint64_t *>(k3_smem + (size_t)N2 * 40);
     for (int i = threadIdx.x; i < N2; i += N2 / 4) s_tw[i] = tb.tw_sub2[i];
-    constexpr int NBOX = N2 >= 1024 ? N2 / 1024 : 1;
-    constexpr int BOX_ROWS = N2 / NBOX;
-    constexpr int CH = BOX_ROWS * 32 < 16384 ? BOX_ROWS * 32 : 16384;    // 1-D bulk copy granule
+    constexpr int CH = N2 * 32 < 16384 ? N2 * 32 : 16384;              // 1-D bulk copy granule
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -227,39 +253,17 @@ k3_pass2(const float2 *__restrict__ mid, const __grid_constant__ CUtensorMap out
     }
     __syncthreads();
     const int c = threadIdx.x & 3, tid = threadIdx.x >> 2;
+    const size_t n1 = (size_t)n_tiles * 4;
     uint32_t phase = 0;
     for (int u = blockIdx.x; u < n_tiles; u += gridDim.x) {
         mbar_wait(bar, phase);
         phase ^= 1;
-        k3_fft_tile<4, N2, true, false>(buf, s_tw, tid, c);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            // buf is [k2][c] dense; out is [k2][k1] with k1 = 4u + c: 32-byte rows
-#pragma unroll
-            for (int b = 0; b < NBOX; ++b) {
-                for (int r0 = b * BOX_ROWS; r0 < (b + 1) * BOX_ROWS; r0 += 256)
-                    tma_store_2d(&out_map, 8 * u, r0, buf + r0 * 4);
-                tma_store_commit();
-            }
-            const int nxt = u + gridDim.x;
-            if (nxt < n_tiles) mbar_expect_tx(bar, N2 * 32);
-            const char *src = reinterpret_cast<const char *>(mid) + (size_t)nxt * N2 * 32;
-#pragma unroll
-            for (int b = 0; b < NBOX; ++b) {
-                switch (NBOX - 1 - b) {
-                    case 0: tma_store_wait_read<0>(); break;
-                    case 1: tma_store_wait_read<1>(); break;
-                    case 2: tma_store_wait_read<2>(); break;
-                    default: tma_store_wait_read<3>(); break;
-                }
-                if (nxt < n_tiles)
-                    for (int off = b * BOX_ROWS * 32; off < (b + 1) * BOX_ROWS * 32; off += CH)
-                        tma_load_1d(k3_smem + off, src + off, CH, bar);
-            }
-        }
+        const int nxt = u + gridDim.x;
+        K3Out2 out{outp + 4 * (size_t)u + c, n1, bar,
+                   nxt < n_tiles ? reinterpret_cast<const char *>(mid) + (size_t)nxt * N2 * 32 : nullptr, k3_smem,
+                   N2 * 32, CH};
+        k3_fft_tile<4, N2, true, false>(buf, s_tw, tid, c, out);
     }
-    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------- host ----
@@ -380,16 +384,16 @@ template <class K> static int k3_grid(K kern, int threads, int smem, int tiles, 
     long long g = (long long)nb * sms;
     return (int)(g < tiles ? g : tiles);
 }
-template <int N1> static cudaError_t launch_pass1(int tiles, int sms, const CUtensorMap &a, const CUtensorMap &b,
-                                                  K3Tables tb, cudaStream_t st) {
+template <int N1> static cudaError_t launch_pass1(int tiles, int sms, const CUtensorMap &a, float2 *mid, K3Tables tb,
+                                                  cudaStream_t st) {
     const int smem = N1 * 24 + 16;
     cudaError_t e = cudaFuncSetAttribute(k3_pass1<N1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    k3_pass1<N1><<<k3_grid(k3_pass1<N1>, N1 / 8, smem, tiles, sms), N1 / 8, smem, st>>>(a, b, tb, tiles);
+    k3_pass1<N1><<<k3_grid(k3_pass1<N1>, N1 / 8, smem, tiles, sms), N1 / 8, smem, st>>>(a, mid, tb, tiles);
     return cudaGetLastError();
 }
-template <int N2> static cudaError_t launch_pass2(int tiles, int sms, const float2 *mid, const CUtensorMap &o,
-                                                  K3Tables tb, cudaStream_t st) {
+template <int N2> static cudaError_t launch_pass2(int tiles, int sms, const float2 *mid, float2 *o, K3Tables tb,
+                                                  cudaStream_t st) {
     const int smem = N2 * 40 + 16;
     cudaError_t e = cudaFuncSetAttribute(k3_pass2<N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
@@ -414,15 +418,12 @@ extern "C" kopek_status kopek_fft_large_c2c_f32(const float *d_in, float *d_out,
     K3Plan p;
     kopek_status st = k3_get_plan(n, device, &p);
     if (st != KOPEK_OK) return st;
-    CUtensorMap in_map, mid_map, out_map;
-    // in:  [N1 rows][N2 complex]          box 2 complex x 256 rows   (pass 1: two-column tiles)
-    // mid: [N1/4 rows][N2*4 complex]      box 8 complex x 256 rows   (tile-major [k1/4][n2/2][k1%4][n2%2], 64-byte segments)
-    // out: [N2 rows][N1 complex]          box 4 complex x 256 rows   (pass 2: four-row tiles; two-row tiles with
-    //                                      16-byte stores were measured slower: 0.184 ms vs 0.162 ms at 2^24)
-    const uint32_t r1 = p.n1 < 256 ? p.n1 : 256, rm = p.n1 / 4 < 256 ? p.n1 / 4 : 256, r2 = p.n2 < 256 ? p.n2 : 256;
-    if (!make_map(&in_map, d_in, 2ull * p.n2, p.n1, 4, r1) ||
-        !make_map(&mid_map, p.mid, 8ull * p.n2, p.n1 / 4, 16, rm) ||
-        !make_map(&out_map, d_out, 2ull * p.n1, p.n2, 8, r2))
+    CUtensorMap in_map;
+    // in:  [N1 rows][N2 complex], box 2 complex x 256 rows (pass 1: two-column tiles).  mid is tile-major
+    // [k1/4][n2/2][k1%4][n2%2] (pass 1 stores 64-byte segments, pass 2 loads one contiguous block per tile); the
+    // output is written in natural order by pass 2 in 32-byte runs.
+    const uint32_t r1 = p.n1 < 256 ? p.n1 : 256;
+    if (!make_map(&in_map, d_in, 2ull * p.n2, p.n1, 4, r1))
         return fail(KOPEK_ERR_CUDA, "cuTensorMapEncodeTiled failed (driver entry point missing or bad geometry)");
     K3Tables tb{p.tw1, p.tw2, p.hi, p.lo};
     cudaStream_t stream = (cudaStream_t)cuda_stream;
@@ -430,19 +431,19 @@ extern "C" kopek_status kopek_fft_large_c2c_f32(const float *d_in, float *d_out,
     KOPEK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     cudaError_t e = cudaErrorInvalidValue;
     switch (p.n1) {
-        case 256: e = launch_pass1<256>(p.n2 / 2, sms, in_map, mid_map, tb, stream); break;
-        case 512: e = launch_pass1<512>(p.n2 / 2, sms, in_map, mid_map, tb, stream); break;
-        case 1024: e = launch_pass1<1024>(p.n2 / 2, sms, in_map, mid_map, tb, stream); break;
-        case 2048: e = launch_pass1<2048>(p.n2 / 2, sms, in_map, mid_map, tb, stream); break;
-        case 4096: e = launch_pass1<4096>(p.n2 / 2, sms, in_map, mid_map, tb, stream); break;
+        case 256: e = launch_pass1<256>(p.n2 / 2, sms, in_map, p.mid, tb, stream); break;
+        case 512: e = launch_pass1<512>(p.n2 / 2, sms, in_map, p.mid, tb, stream); break;
+        case 1024: e = launch_pass1<1024>(p.n2 / 2, sms, in_map, p.mid, tb, stream); break;
+        case 2048: e = launch_pass1<2048>(p.n2 / 2, sms, in_map, p.mid, tb, stream); break;
+        case 4096: e = launch_pass1<4096>(p.n2 / 2, sms, in_map, p.mid, tb, stream); break;
     }
     if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "four-step pass 1 (N1=%d): %s", p.n1, cudaGetErrorString(e));
     switch (p.n2) {
-        case 256: e = launch_pass2<256>(p.n1 / 4, sms, p.mid, out_map, tb, stream); break;
-        case 512: e = launch_pass2<512>(p.n1 / 4, sms, p.mid, out_map, tb, stream); break;
-        case 1024: e = launch_pass2<1024>(p.n1 / 4, sms, p.mid, out_map, tb, stream); break;
-        case 2048: e = launch_pass2<2048>(p.n1 / 4, sms, p.mid, out_map, tb, stream); break;
-        case 4096: e = launch_pass2<4096>(p.n1 / 4, sms, p.mid, out_map, tb, stream); break;
+        case 256: e = launch_pass2<256>(p.n1 / 4, sms, p.mid, reinterpret_cast<float2 *>(d_out), tb, stream); break;
+        case 512: e = launch_pass2<512>(p.n1 / 4, sms, p.mid, reinterpret_cast<float2 *>(d_out), tb, stream); break;
+        case 1024: e = launch_pass2<1024>(p.n1 / 4, sms, p.mid, reinterpret_cast<float2 *>(d_out), tb, stream); break;
+        case 2048: e = launch_pass2<2048>(p.n1 / 4, sms, p.mid, reinterpret_cast<float2 *>(d_out), tb, stream); break;
+        case 4096: e = launch_pass2<4096>(p.n1 / 4, sms, p.mid, reinterpret_cast<float2 *>(d_out), tb, stream); break;
         default: e = cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "four-step pass 2 (N2=%d): %s", p.n2, cudaGetErrorString(e));
