@@ -158,6 +158,23 @@ KOPEK_API kopek_status kopek_synth_frames(float *d_out, uint64_t n_frames, uint3
                                           uint32_t freq_mod, uint32_t noise, float noise_gain, uint64_t seed,
                                           uint64_t first_frame, int device, void *cuda_stream);
 
+/* ---- 2c'. decoder-side callers on i16 PCM frames (kopek::decoder::decode returns Vec<[i16; 2]>, src/decoder.rs:1-31) ----
+ * kopek_pcm16_to_f32: the marshalling of examples/graph/player.rs:56-59 -- frame[channel] as f64 / divisor (i16::MAX
+ * there), narrowed once to f32 -- from n_frames interleaved frames of `channels` i16 into the f32 sample buffer the
+ * STFT plans transform.  Bit-exact.  d_pcm 2-byte, d_out 4-byte aligned (16-byte aligned stereo takes the vector path).
+ * kopek_detect_bpm: detect_bpm of src/decoder.rs:39-71 on device-resident stereo frames (16-byte aligned): one-second
+ * windows of 44100 frames (hard coded in the reference), 43 blocks of 1024 frames each, a block is a beat when its
+ * energy exceeds 5.5 x the second's mean block energy; *bpm_out = beats * (60 / duration) in u32 arithmetic.  Every
+ * f32 sum is folded in the reference's order, so block energies, averages, beats and bpm are bit-identical to it.
+ * Where the Rust original panics (less than one second: 60 / 0; sample_rate < 44100: slice index out of range)
+ * this returns KOPEK_ERR_INVALID.  d_block_e (duration*43 f32) and d_avg_e (duration f32) are optional outputs.
+ * Synchronous: returns after the count has been read back. */
+KOPEK_API kopek_status kopek_pcm16_to_f32(const int16_t *d_pcm, uint64_t n_frames, uint32_t channels, uint32_t channel,
+                                          double divisor, float *d_out, int device, void *cuda_stream);
+KOPEK_API kopek_status kopek_detect_bpm(const int16_t *d_frames, uint64_t n_frames, float sample_rate, uint32_t *bpm_out,
+                                        uint32_t *beats_out, float *d_block_e, float *d_avg_e, int device,
+                                        void *cuda_stream);
+
 /* ---- 2d. peer-direct spectrogram (multi-GPU, one process per GPU) -------------------------------
  * When the caller wants ONE spectrogram on one GPU, the other ranks do not send their spectra after
  * the fact: they run kopek_stft_exec with d_out pointing INTO the owner's buffer, mapped through CUDA

@@ -70,6 +70,22 @@ def synth_frames_device(d_out: int, n_frames: int, n: int, sample_rate: float, w
                                          stream or None))
 
 
+def pcm16_to_f32_device(d_pcm: int, n_frames: int, d_out: int, channels: int = 2, channel: int = 0,
+                        divisor: float = 32767.0, device: int = 0, stream: int = 0) -> None:
+    """kopek_pcm16_to_f32: frame[channel] as f64 / i16::MAX (examples/graph/player.rs:56-59), device pointers."""
+    check(_lib.load().kopek_pcm16_to_f32(d_pcm, n_frames, channels, channel, divisor, d_out, device, stream or None))
+
+
+def detect_bpm_device(d_frames: int, n_frames: int, sample_rate: float = 44100.0, d_block_e: int = 0, d_avg_e: int = 0,
+                      device: int = 0, stream: int = 0):
+    """kopek_detect_bpm: kopek::decoder::detect_bpm (src/decoder.rs:39-71) on device-resident [n][2] i16 frames.
+    Returns (bpm, beats)."""
+    bpm, beats = C.c_uint32(0), C.c_uint32(0)
+    check(_lib.load().kopek_detect_bpm(d_frames, n_frames, sample_rate, C.byref(bpm), C.byref(beats), d_block_e or None,
+                                       d_avg_e or None, device, stream or None))
+    return int(bpm.value), int(beats.value)
+
+
 def show_format(label: str, buf) -> str:
     a = np.ascontiguousarray(buf, dtype=np.complex128).reshape(-1)
     lib = _lib.load()

@@ -61,6 +61,9 @@ def lib() -> C.CDLL:
         L.oracle_stft_complex.argtypes = [vp, sz, sz, sz, i32, sz, i32, i32, vp]
         L.oracle_stft_mag.argtypes = [vp, sz, sz, sz, i32, sz, i32, i32, vp]
         L.oracle_max_threads.restype = i32
+        L.oracle_pcm16_to_f32.argtypes = [vp, sz, sz, sz, f64, vp]
+        L.oracle_detect_bpm.restype = C.c_int64
+        L.oracle_detect_bpm.argtypes = [vp, sz, f32, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -193,3 +196,25 @@ def stft_mag(samples, n: int, hop: int, window: int = WIN_RECT, bins: int | None
 
 def max_threads() -> int:
     return int(lib().oracle_max_threads())
+
+
+def pcm16_to_f32(pcm, channel: int = 0, divisor: float = 32767.0) -> np.ndarray:
+    """examples/graph/player.rs:56-59: frame[channel] as f64 / i16::MAX, narrowed once to f32."""
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+    if pcm.ndim == 1:
+        pcm = pcm[:, None]
+    out = np.empty(pcm.shape[0], dtype=np.float32)
+    lib().oracle_pcm16_to_f32(_p(pcm), pcm.shape[0], pcm.shape[1], channel, divisor, _p(out))
+    return out
+
+
+def detect_bpm(frames, sample_rate: float = 44100.0):
+    """src/decoder.rs:39-71.  frames: [n][2] int16.  Returns (bpm, beats, block_e[duration*43], avg_e[duration]);
+    bpm is None where the Rust original panics (duration 0, or fewer than duration*44100 frames)."""
+    frames = np.ascontiguousarray(frames, dtype=np.int16).reshape(-1, 2)
+    duration = int(np.float32(frames.shape[0]) / np.float32(sample_rate))
+    block_e = np.zeros(max(duration, 0) * 43, dtype=np.float32)
+    avg_e = np.zeros(max(duration, 0), dtype=np.float32)
+    beats = C.c_uint32(0)
+    bpm = lib().oracle_detect_bpm(_p(frames), frames.shape[0], sample_rate, C.byref(beats), _p(block_e), _p(avg_e))
+    return (None if bpm < 0 else int(bpm)), int(beats.value), block_e, avg_e

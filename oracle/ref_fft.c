@@ -386,3 +386,57 @@ ORACLE_API void oracle_stft_mag(const float *samples, size_t n_samples, size_t n
                                 size_t bins, int output, int threads, float *out) {
     stft_run(samples, n_samples, n, hop, window, bins, 64, output, threads, out);
 }
+
+/* ------------------------------------------------- decoder-side callers --- */
+
+/* i16 frame -> the f32 sample the f32 pipeline transforms.  examples/graph/player.rs:56-59:
+ *   frame[0] as f64 / std::i16::MAX as f64            (f64 division, then our f32 path narrows once)
+ * pcm: n_frames x channels interleaved; out[i] = (float)((double)pcm[i*channels + channel] / divisor). */
+ORACLE_API void oracle_pcm16_to_f32(const int16_t *pcm, size_t n_frames, size_t channels, size_t channel,
+                                    double divisor, float *out) {
+    for (size_t i = 0; i < n_frames; ++i) out[i] = (float)((double)pcm[i * channels + channel] / divisor);
+}
+
+/* detect_bpm, src/decoder.rs:39-71, statement by statement.
+ *   f_frames = frames.map(|f| [f[0] as f32 / i16::MAX as f32, f[1] as f32 / i16::MAX as f32])     :41-44
+ *   duration = (frames.len() as f32 / sample_rate) as usize                                        :46 (:35-37)
+ *   for i in 0..duration: start = i*44100, end = (i+1)*44100      (44100 is hard coded)            :48-50
+ *     average_e = sum_{start..end} (f[0].powf(2.0) + f[1].powf(2.0))   sequential f32 fold from 0  :51-53
+ *     average_e *= 1024.0 / 44100.0                                                                :54
+ *     for j in 0..43: e = the same sum over the 1024 frames of block j; if e > C*average_e: beats  :57-66
+ *   beats * (60 / duration as u32)                                    u32 division                 :70
+ * powf(x, 2.0) is x*x correctly rounded.  The Rust original panics when duration == 0 (division by zero) or when
+ * duration*44100 exceeds the slice (sample_rate < 44100): both return -1 here.  block_e (duration*43) and avg_e
+ * (duration, already scaled) are optional outputs for the parity tests.  Returns bpm, *beats_out = beats. */
+ORACLE_API int64_t oracle_detect_bpm(const int16_t *frames, size_t n_frames, float sample_rate, uint32_t *beats_out,
+                                     float *block_e, float *avg_e) {
+    const float C = 5.5f, imax = (float)INT16_MAX;
+    const size_t duration = (size_t)((float)n_frames / sample_rate);
+    if (duration == 0 || duration * 44100 > n_frames) return -1;
+    uint32_t beats = 0;
+    for (size_t i = 0; i < duration; ++i) {
+        const int16_t *sec = frames + 2 * i * 44100;
+        float average_e = 0.0f;
+        for (size_t k = 0; k < 44100; ++k) {
+            float a = (float)sec[2 * k] / imax, b = (float)sec[2 * k + 1] / imax;
+            float a2 = a * a, b2 = b * b;
+            float s = a2 + b2;
+            average_e = average_e + s;
+        }
+        average_e = average_e * (1024.0f / 44100.0f);
+        if (avg_e) avg_e[i] = average_e;
+        for (size_t j = 0; j < 43; ++j) {
+            float e = 0.0f;
+            for (size_t k = j * 1024; k < (j + 1) * 1024; ++k) {
+                float a = (float)sec[2 * k] / imax, b = (float)sec[2 * k + 1] / imax;
+                float a2 = a * a, b2 = b * b;
+                float s = a2 + b2;
+                e = e + s;
+            }
+            if (block_e) block_e[i * 43 + j] = e;
+            if (e > C * average_e) beats += 1;
+        }
+    }
+    if (beats_out) *beats_out = beats;
+    return (int64_t)(beats * (60u / (uint32_t)duration));
+}

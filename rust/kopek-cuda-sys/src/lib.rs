@@ -74,6 +74,11 @@ extern "C" {
     pub fn kopek_synth_frames(d_out: *mut f32, n_frames: u64, n: u32, stride: u64, sample_rate: f32, wave: u32,
                               duty: f32, freq0: f32, freq_step: f32, freq_mod: u32, noise: u32, noise_gain: f32,
                               seed: u64, first_frame: u64, device: c_int, cuda_stream: *mut c_void) -> kopek_status;
+    pub fn kopek_pcm16_to_f32(d_pcm: *const i16, n_frames: u64, channels: u32, channel: u32, divisor: f64,
+                              d_out: *mut f32, device: c_int, cuda_stream: *mut c_void) -> kopek_status;
+    pub fn kopek_detect_bpm(d_frames: *const i16, n_frames: u64, sample_rate: f32, bpm_out: *mut u32,
+                            beats_out: *mut u32, d_block_e: *mut f32, d_avg_e: *mut f32, device: c_int,
+                            cuda_stream: *mut c_void) -> kopek_status;
     pub fn kopek_device_alloc(d_ptr: *mut *mut c_void, bytes: usize, device: c_int) -> kopek_status;
     pub fn kopek_device_free(d_ptr: *mut c_void, device: c_int) -> kopek_status;
     pub fn kopek_copy(dst: *mut c_void, src: *const c_void, bytes: usize, device: c_int) -> kopek_status;

@@ -1,0 +1,82 @@
+"""GPU: the decoder-side callers through the C ABI against the oracle -- bit-exact.
+
+kopek_pcm16_to_f32 = examples/graph/player.rs:56-59 (frame[0] as f64 / i16::MAX); kopek_detect_bpm = src/decoder.rs:39-71."""
+import numpy as np
+import pytest
+
+from test_oracle import _click_track
+from util import frame_rel_err, tol
+
+pytestmark = pytest.mark.gpu
+
+
+def test_pcm16_to_f32_is_bit_exact(built_lib, oracle_mod):
+    import torch
+    from kopek_b200 import fft, KopekError
+    rng = np.random.default_rng(3)
+    for channels, n, offset in ((2, 100003, 0), (2, 4099, 1), (1, 5000, 0), (3, 777, 0), (2, 3, 0)):
+        pcm = rng.integers(-32768, 32768, size=(n + offset, channels), dtype=np.int16)
+        pcm[offset:offset + 3, 0] = [32767, -32768, 0]
+        d = torch.from_numpy(pcm).cuda()
+        for ch in range(channels):
+            out = torch.full((n + 8,), float("nan"), device="cuda")
+            fft.pcm16_to_f32_device(d.data_ptr() + offset * channels * 2, n, out.data_ptr(), channels, ch)
+            torch.cuda.synchronize()
+            got = out.cpu().numpy()
+            np.testing.assert_array_equal(got[:n], oracle_mod.pcm16_to_f32(pcm[offset:], ch))
+            assert np.isnan(got[n:]).all()
+    with pytest.raises(KopekError):
+        fft.pcm16_to_f32_device(d.data_ptr(), 3, out.data_ptr(), 2, 2)          # channel out of range
+    with pytest.raises(KopekError):
+        fft.pcm16_to_f32_device(d.data_ptr(), 3, out.data_ptr(), 2, 0, divisor=0.0)
+
+
+@pytest.mark.parametrize("seconds,bpm,seed", [(3.2, 120, 0), (7.9, 90, 1), (1.0, 60, 2), (12.5, 174, 3), (61.5, 128, 4),
+                                              (300.0, 100, 5)])
+def test_detect_bpm_is_bit_exact(built_lib, oracle_mod, seconds, bpm, seed):
+    import torch
+    from kopek_b200 import fft
+    x = _click_track(seconds, bpm, seed)
+    ref_bpm, ref_beats, ref_block, ref_avg = oracle_mod.detect_bpm(x)
+    d = torch.from_numpy(x).cuda()
+    be = torch.full((ref_block.size + 4,), float("nan"), device="cuda")
+    av = torch.full((ref_avg.size + 4,), float("nan"), device="cuda")
+    got_bpm, got_beats = fft.detect_bpm_device(d.data_ptr(), x.shape[0], 44100.0, be.data_ptr(), av.data_ptr())
+    assert (got_bpm, got_beats) == (ref_bpm, ref_beats)
+    np.testing.assert_array_equal(be.cpu().numpy()[:ref_block.size], ref_block)
+    np.testing.assert_array_equal(av.cpu().numpy()[:ref_avg.size], ref_avg)
+    assert np.isnan(be.cpu().numpy()[ref_block.size:]).all() and np.isnan(av.cpu().numpy()[ref_avg.size:]).all()
+    # without the optional outputs
+    assert fft.detect_bpm_device(d.data_ptr(), x.shape[0]) == (ref_bpm, ref_beats)
+    if seconds > 60:
+        assert got_bpm == 0 and got_beats > 0        # 60 / duration == 0 in u32 arithmetic (decoder.rs:70)
+
+
+def test_detect_bpm_rejects_what_the_reference_panics_on(built_lib):
+    import torch
+    from kopek_b200 import fft, KopekError
+    d = torch.zeros((50000, 2), dtype=torch.int16, device="cuda")
+    with pytest.raises(KopekError):
+        fft.detect_bpm_device(d.data_ptr(), 30000)                  # duration 0 -> 60 / 0
+    with pytest.raises(KopekError):
+        fft.detect_bpm_device(d.data_ptr(), 50000, 22050.0)         # 2 "seconds" x 44100 frames > 50000
+    assert fft.detect_bpm_device(d.data_ptr(), 50000) == (0, 0)     # silence: 0 > 0 is false
+
+
+def test_decoded_frames_to_spectrum(built_lib, oracle_mod):
+    """The graph player's path end to end (examples/graph/player.rs:56-61, utils.rs:47-63): i16 frames -> channel 0 /
+    32767 -> fft -> magnitude, on device, against the f64 oracle."""
+    import torch
+    from kopek_b200 import fft, StftPlan, OUT_MAG, WINDOW_RECT
+    n, frames = 1024, 37
+    x = _click_track(1.0, 140, 7)[: n * frames]
+    d = torch.from_numpy(x).cuda()
+    samples = torch.empty(n * frames, device="cuda")
+    fft.pcm16_to_f32_device(d.data_ptr(), n * frames, samples.data_ptr(), 2, 0)
+    out = torch.empty((frames, n // 2 + 1), device="cuda")
+    with StftPlan(n, n, WINDOW_RECT, OUT_MAG) as plan:
+        plan.exec_ptr(samples.data_ptr(), n * frames, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ref = np.stack([oracle_mod.mag_norm(oracle_mod.fft(oracle_mod.marshal(x[f * n:(f + 1) * n, 0].astype(np.float32), 32767.0)))
+                    [: n // 2 + 1] for f in range(frames)])
+    assert frame_rel_err(out.cpu().numpy().astype(np.float64), ref) <= tol(n)

@@ -84,6 +84,21 @@ for lg in (20, 22, 24):
     b = torch.empty_like(a)
     ms = timed(lambda: fft.fft_large_device(a.data_ptr(), b.data_ptr(), n, 0, st))
     rows.append((f"cfg3: single 2^{lg} c2c f32 four-step (K3)", "1 transform", ms, 2 * n * 8, n / ms / 1e6))
+# decoder-side callers: i16 stereo frames as kopek::decoder::decode returns them
+dec_rows = []
+nfr = 1 << 28
+pcm = torch.randint(-32768, 32767, (nfr, 2), dtype=torch.int16, device="cuda")
+o32 = torch.empty(nfr, device="cuda")
+ms = timed(lambda: fft.pcm16_to_f32_device(pcm.data_ptr(), nfr, o32.data_ptr(), 2, 0, stream=st), iters=10)
+dec_rows.append((f"pcm16 -> f32, channel 0 / 32767 (f64 division), 2^28 stereo frames", ms, nfr * 8))
+del o32
+hour = 3600 * 44100
+ms = timed(lambda: fft.detect_bpm_device(pcm.data_ptr(), hour, 44100.0, stream=st), iters=5, warm=1)
+dec_rows.append((f"detect_bpm, 1 h of 44.1 kHz stereo (sequential f32 folds, bit-exact)", ms, hour * 4))
+ms = timed(lambda: fft.detect_bpm_device(pcm.data_ptr(), 124443, 44100.0, stream=st), iters=5, warm=1)
+dec_rows.append((f"detect_bpm, 2.8 s clip (the reference's sample.wav size): latency", ms, 124443 * 4))
+del pcm
+torch.cuda.empty_cache()
 # configs[0]: host-to-host latency of one drop-in call
 x = (np.random.default_rng(0).standard_normal(1024)).astype(np.complex128)
 fft.fft(x)
@@ -98,4 +113,7 @@ for name, units, ms, by, gs in rows:
 print("\n| library bar (not the product) | ms | algorithmic GB/s | % | G samples/s |\n|---|---:|---:|---:|---:|")
 for name, ms, by, gs in lib_rows:
     print(f"| {name} | {ms:.4f} | {by / ms / 1e6:.1f} | {100 * by / ms / 1e6 / PEAK:.1f} | {gs:.1f} |")
+print("\n| decoder-side callers | ms | algorithmic GB/s | % |\n|---|---:|---:|---:|")
+for name, ms, by in dec_rows:
+    print(f"| {name} | {ms:.4f} | {by / ms / 1e6:.1f} | {100 * by / ms / 1e6 / PEAK:.1f} |")
 print(f"\ncfg0: one 1024-pt fft() drop-in call, host buffers in/out (K2): {lat:.1f} us per call")
