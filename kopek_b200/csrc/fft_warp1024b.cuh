@@ -121,35 +121,92 @@ k1w_1024b_kernel(const K1WParams p) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) b[i] = zR[32 * (7 - i)];
         if (k1 == 0) b[0] = par ? zu[0] : zl[0];            // k = 128 pairs with Z[384] (own upper 0); k = 0 with itself
-        constexpr int EB = OUT == OUT_COMPLEX ? 8 : 4;
-        char *o_lo = reinterpret_cast<char *>(p.out) + (frame * p.pitch + (k1 + 128 * par)) * EB;
-        char *o_hi = reinterpret_cast<char *>(p.out) + (frame * p.pitch + (M - k1 - 128 * par)) * EB;
-        if constexpr (BULK) {
-            // the staging buffer is the warp's own and is never touched by the exchanges of the next frame
-            if (l == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous frame has left
-            __syncwarp();
-            o_lo = reinterpret_cast<char *>(stage + (k1 + 128 * par));
-            o_hi = reinterpret_cast<char *>(stage + (M - k1 - 128 * par));
-        }
+        constexpr bool BANDS = OUT == OUT_BANDS_LOG || OUT == OUT_BANDS_LOW;
+        if constexpr (BANDS) {
+            // Fused band epilogue: scale |X| joins the eight band means of
+            // examples/graph/utils.rs:85-116 (log set [0,4) [4,8) [8,16) ... [256,512)) or examples/pong/utils.rs:96-114
+            // (eight 3-bin bands from bin 20); 40 bytes leave the SM per frame instead of 2052.
+            // This lane's bins: k = k1 + 128 par + 16 i and M - k.  par = 1: k in [128, 256) = log band 6 for every i;
+            // par = 0: i = 0 -> bands 0..2 by k1, i = 1 -> band 3, i = 2, 3 -> band 4, i >= 4 -> band 5; M - k is band 7.
+            constexpr float ysc = WIN ? 1.0f : 0.5f;
+            float part[4] = {0.f, 0.f, 0.f, 0.f};            // i = 0 | i = 1 | i = 2, 3 | i >= 4
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float2 A = zl[i], B = b[i];
-            float2 S = make_float2(A.x + B.x, A.y - B.y);
-            float2 D = make_float2(A.x - B.x, A.y + B.y);
-            float2 Q = cmul(mul_w64(D, i), pw_lane);        // -i W1024^{k1 + 128 par + 16 i}
-            emit_at<OUT, WIN>(o_lo + 16 * i * EB, S + Q);
-            emit_at<OUT, WIN>(o_hi - 16 * i * EB, make_float2(S.x - Q.x, Q.y - S.y));
-        }
-        if (l == 0) emit_at<OUT, WIN>(o_lo + (M / 2) * EB, make_float2(2.0f * zu[0].x, -2.0f * zu[0].y));   // bin 256
-        if constexpr (BULK) {
-            __syncwarp();
+            for (int i = 0; i < 8; ++i) {
+                if (OUT == OUT_BANDS_LOW && (i == 0 || i > 2)) continue;       // bins 20..43 only: i = 1, 2 of the par = 0 lanes
+                const float2 A = zl[i], B = b[i];
+                float2 S = make_float2(A.x + B.x, A.y - B.y);
+                float2 D = make_float2(A.x - B.x, A.y + B.y);
+                float2 Q = cmul(mul_w64(D, i), pw_lane);
+                const float2 X1 = S + Q;
+                const float y1 = ysc * fast_sqrt(X1.x * X1.x + X1.y * X1.y);
+                if constexpr (OUT == OUT_BANDS_LOG) {
+                    part[i == 0 ? 0 : i == 1 ? 1 : i < 4 ? 2 : 3] += y1;
+                    const float2 X2 = make_float2(S.x - Q.x, Q.y - S.y);
+                    const float y2 = ysc * fast_sqrt(X2.x * X2.x + X2.y * X2.y);
+                    acc[7] += (i == 0 && l == 0) ? 0.0f : y2;                  // k = 0 pairs with bin 512: not in a band
+                } else {
+                    band_add<0, 7>(acc, par ? -1 : band_low_of(k1 + 16 * i), y1);
+                }
+            }
+            if constexpr (OUT == OUT_BANDS_LOG) {
+                acc[6] = par ? part[0] + part[1] + part[2] + part[3] : 0.0f;
+                acc[5] = par ? 0.0f : part[3];
+                acc[4] = par ? 0.0f : part[2];
+                acc[3] = par ? 0.0f : part[1];
+                band_add<0, 2>(acc, par ? -1 : band_log_of(k1), part[0]);
+                if (l == 0) acc[7] += 2.0f * ysc * fast_sqrt(zu[0].x * zu[0].x + zu[0].y * zu[0].y);   // bin 256
+            }
+#pragma unroll
+            for (int bnd = 0; bnd < 8; ++bnd) {
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) acc[bnd] += __shfl_xor_sync(0xffffffffu, acc[bnd], sft);
+            }
             if (l == 0) {
+                constexpr float inv_log[8] = {1.f / 4, 1.f / 4, 1.f / 8, 1.f / 16, 1.f / 32, 1.f / 64, 1.f / 128, 1.f / 256};
                 float *row = reinterpret_cast<float *>(p.out) + frame * p.pitch;
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 2048;" ::"l"(row),
-                             "r"(k1b_smem_u32(stage)) : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                row[M] = stage[M];                             // bin 512: the 513th value of the row
+                float mx = 0.0f;
+                int idx = 0;
+#pragma unroll
+                for (int bnd = 0; bnd < 8; ++bnd) {
+                    float m = acc[bnd] * p.band_scale * (OUT == OUT_BANDS_LOG ? inv_log[bnd] : (1.0f / 3.0f));
+                    row[bnd] = m;
+                    if (m > mx) { mx = m; idx = bnd; }                          // examples/pong/main.rs:200-207
+                }
+                row[8] = (float)idx;
+                row[9] = mx;
+            }
+        } else {
+            constexpr int EB = OUT == OUT_COMPLEX ? 8 : 4;
+            char *o_lo = reinterpret_cast<char *>(p.out) + (frame * p.pitch + (k1 + 128 * par)) * EB;
+            char *o_hi = reinterpret_cast<char *>(p.out) + (frame * p.pitch + (M - k1 - 128 * par)) * EB;
+            if constexpr (BULK) {
+                // the staging buffer is the warp's own and is never touched by the exchanges of the next frame
+                if (l == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous frame has left
+                __syncwarp();
+                o_lo = reinterpret_cast<char *>(stage + (k1 + 128 * par));
+                o_hi = reinterpret_cast<char *>(stage + (M - k1 - 128 * par));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float2 A = zl[i], B = b[i];
+                float2 S = make_float2(A.x + B.x, A.y - B.y);
+                float2 D = make_float2(A.x - B.x, A.y + B.y);
+                float2 Q = cmul(mul_w64(D, i), pw_lane);        // -i W1024^{k1 + 128 par + 16 i}
+                emit_at<OUT, WIN>(o_lo + 16 * i * EB, S + Q);
+                emit_at<OUT, WIN>(o_hi - 16 * i * EB, make_float2(S.x - Q.x, Q.y - S.y));
+            }
+            if (l == 0) emit_at<OUT, WIN>(o_lo + (M / 2) * EB, make_float2(2.0f * zu[0].x, -2.0f * zu[0].y));   // bin 256
+            if constexpr (BULK) {
+                __syncwarp();
+                if (l == 0) {
+                    float *row = reinterpret_cast<float *>(p.out) + frame * p.pitch;
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 2048;" ::"l"(row),
+                                 "r"(k1b_smem_u32(stage)) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    row[M] = stage[M];                             // bin 512: the 513th value of the row
+                }
             }
         }
         __syncwarp();

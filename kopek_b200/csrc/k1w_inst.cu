@@ -1,4 +1,5 @@
-// Instantiations + host launcher of the warp-per-frame 1024-point kernel (fft_warp1024.cuh).
+// Instantiations + host launchers of the lane-group kernels: 1024 points (fft_warp1024b.cuh; the three-pass
+// fft_warp1024.cuh in tuning builds), 256 points (fft_warp256.cuh), 512 points (fft_warp512.cuh).
 #include <math.h>
 
 #include <vector>
@@ -8,6 +9,7 @@
 
 namespace kopek {
 
+#ifdef KOPEK_K1W_SWEEP   // the three-pass kernel of fft_warp1024.cuh: tuning builds only (tools/sweep_k1w.py)
 // Host-side tables, built in f64 and rounded once to f32 (layout: see fft_warp1024.cuh).
 void k1w_build_tables(const float *half_window /* 1024 or nullptr */, float4 *out) {
     const double tau = 2.0 * M_PI;
@@ -113,6 +115,8 @@ cudaError_t k1w_launch(const K1WParams &p, int output, bool win, int variant, in
     }
 }
 
+#endif  // KOPEK_K1W_SWEEP
+
 // ------------------------------------------------------------------ 1024-point, two-exchange kernel ----
 void k1b_build_tables(const float *half_window /* 1024 or nullptr */, float4 *out4) {
     float2 *out = reinterpret_cast<float2 *>(out4);
@@ -175,6 +179,10 @@ cudaError_t k1b_launch(const K1WParams &p, int output, bool win, bool bulk, int 
         case 5: return launch1b<OUT_POWER, true>(p, grid, stream, occ_out);
         case 6: return launch1b<OUT_DB, false>(p, grid, stream, occ_out);
         case 7: return launch1b<OUT_DB, true>(p, grid, stream, occ_out);
+        case 8: return launch1b<OUT_BANDS_LOG, false>(p, grid, stream, occ_out);
+        case 9: return launch1b<OUT_BANDS_LOG, true>(p, grid, stream, occ_out);
+        case 10: return launch1b<OUT_BANDS_LOW, false>(p, grid, stream, occ_out);
+        case 11: return launch1b<OUT_BANDS_LOW, true>(p, grid, stream, occ_out);
         default: return cudaErrorInvalidValue;
     }
 }

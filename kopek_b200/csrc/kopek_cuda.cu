@@ -230,7 +230,7 @@ struct kopek_plan {
     k1_launch_fn launch;
     float *d_win;      // 0.5 * w
     float2 *d_tw, *d_pw;
-    float4 *d_k1w;     // tables of the warp-per-frame kernels (n == 256 / 512 / 1024)
+    float4 *d_k1w;     // tables of the sub-warp kernels (n == 256 / 512); n == 1024: the three-pass kernel in tuning builds
     float4 *d_k1b;     // tables of the two-exchange 1024-point kernel
     int k1b_warps_per_sm;
     float4 *d_k1m;     // tables of the team-per-frame kernel (n == 2048 / 4096; n == 1024 with KOPEK_K1W_VARIANT=300)
@@ -268,16 +268,19 @@ static kopek_status upload_window(kopek_plan *p, const float *w) {
         k1m_build_tables((int)p->n, half.data(), cs_a, cs_b, t.data());
         KOPEK_CUDA(cudaMemcpy(p->d_k1m, t.data(), sizeof(float4) * t.size(), cudaMemcpyHostToDevice));
     }
+    if (p->d_k1b) {
+        std::vector<float4> tb(K1B_TABLE_F4);
+        k1b_build_tables(half.data(), tb.data());
+        KOPEK_CUDA(cudaMemcpy(p->d_k1b, tb.data(), sizeof(float4) * K1B_TABLE_F4, cudaMemcpyHostToDevice));
+    }
+#ifdef KOPEK_K1W_SWEEP
     if (p->d_k1w && p->n == 1024) {
         std::vector<float4> t(K1W_TABLE_F4);
         k1w_build_tables(half.data(), t.data());
         KOPEK_CUDA(cudaMemcpy(p->d_k1w, t.data(), sizeof(float4) * K1W_TABLE_F4, cudaMemcpyHostToDevice));
-        if (p->d_k1b) {
-            std::vector<float4> tb(K1B_TABLE_F4);
-            k1b_build_tables(half.data(), tb.data());
-            KOPEK_CUDA(cudaMemcpy(p->d_k1b, tb.data(), sizeof(float4) * K1B_TABLE_F4, cudaMemcpyHostToDevice));
-        }
-    } else if (p->d_k1w && p->n == 256) {
+    }
+#endif
+    if (p->d_k1w && p->n == 256) {
         std::vector<float4> t(K1W256_TABLE_F4);
         k1w256_build_tables(half.data(), t.data());
         KOPEK_CUDA(cudaMemcpy(p->d_k1w, t.data(), sizeof(float4) * K1W256_TABLE_F4, cudaMemcpyHostToDevice));
@@ -462,38 +465,42 @@ kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint
             break;
         }
         if (n == 1024) {
-            // headline size: warp-per-frame kernel (fft_warp1024.cuh); K1 stays for FULL bins / odd hops
+            // headline size: the two-exchange warp-per-frame kernel (fft_warp1024b.cuh), every output; K1 stays for
+            // FULL bins / odd hops.  KOPEK_K1W_VARIANT (tuning): < 0 generic K1, 300 team kernel with R = 2,
+            // 0..13 the three-pass kernel of fft_warp1024.cuh (only in -DKOPEK_K1W_SWEEP builds).
             const char *env = getenv("KOPEK_K1W_VARIANT");
-            p->k1w_variant = env ? atoi(env) : 200;      // 200 = the two-exchange kernel; 0..13 / <0: tuning only
-            const int setup_variant = p->k1w_variant >= 200 ? 0 : p->k1w_variant;
-            if (p->k1w_variant >= 0 || bands) {
-                if (p->k1w_variant < 0) p->k1w_variant = 0;
+            p->k1w_variant = env ? atoi(env) : 200;
+#ifndef KOPEK_K1W_SWEEP
+            if (p->k1w_variant >= 0) p->k1w_variant = std::max(p->k1w_variant, 200);
+#endif
+            if (p->k1w_variant < 0 && bands) p->k1w_variant = 200;      // the generic kernel has no band epilogue
+            K1WParams dummy{};
+#ifdef KOPEK_K1W_SWEEP
+            if (p->k1w_variant >= 0 && p->k1w_variant < 200) {
                 std::vector<float4> t(K1W_TABLE_F4);
                 k1w_build_tables(nullptr, t.data());
                 if ((e = cudaMalloc(&p->d_k1w, sizeof(float4) * K1W_TABLE_F4)) != cudaSuccess ||
                     (e = cudaMemcpy(p->d_k1w, t.data(), sizeof(float4) * K1W_TABLE_F4, cudaMemcpyHostToDevice)) !=
-                        cudaSuccess) {
-                    st = fail(KOPEK_ERR_CUDA, "K1W table upload failed: %s", cudaGetErrorString(e));
+                        cudaSuccess ||
+                    (e = k1w_launch(dummy, (int)output, window != KOPEK_WINDOW_RECT, p->k1w_variant, 0, nullptr,
+                                    &p->k1w_warps_per_sm)) != cudaSuccess ||
+                    p->k1w_warps_per_sm <= 0) {
+                    st = fail(KOPEK_ERR_CUDA, "K1W setup failed: %s", cudaGetErrorString(e));
                     break;
                 }
-                K1WParams dummy{};
-                e = k1w_launch(dummy, (int)output, window != KOPEK_WINDOW_RECT, setup_variant, 0, nullptr,
-                               &p->k1w_warps_per_sm);
-                if (e != cudaSuccess || p->k1w_warps_per_sm <= 0) {
-                    st = fail(KOPEK_ERR_CUDA, "K1W kernel cannot be resident: %s", cudaGetErrorString(e));
+            }
+#endif
+            if (p->k1w_variant >= 200) {
+                std::vector<float4> tb(K1B_TABLE_F4);
+                k1b_build_tables(nullptr, tb.data());
+                if ((e = cudaMalloc(&p->d_k1b, sizeof(float4) * K1B_TABLE_F4)) != cudaSuccess ||
+                    (e = cudaMemcpy(p->d_k1b, tb.data(), sizeof(float4) * K1B_TABLE_F4, cudaMemcpyHostToDevice)) !=
+                        cudaSuccess ||
+                    (e = k1b_launch(dummy, (int)output, window != KOPEK_WINDOW_RECT, false, 0, nullptr,
+                                    &p->k1b_warps_per_sm)) != cudaSuccess ||
+                    p->k1b_warps_per_sm <= 0) {
+                    st = fail(KOPEK_ERR_CUDA, "K1W-1024b setup failed: %s", cudaGetErrorString(e));
                     break;
-                }
-                if (output <= KOPEK_OUT_DB) {       // two-exchange kernel (fft_warp1024b.cuh) for the spectrum outputs
-                    std::vector<float4> tb(K1B_TABLE_F4);
-                    k1b_build_tables(nullptr, tb.data());
-                    if ((e = cudaMalloc(&p->d_k1b, sizeof(float4) * K1B_TABLE_F4)) != cudaSuccess ||
-                        (e = cudaMemcpy(p->d_k1b, tb.data(), sizeof(float4) * K1B_TABLE_F4, cudaMemcpyHostToDevice)) !=
-                            cudaSuccess ||
-                        (e = k1b_launch(dummy, (int)output, window != KOPEK_WINDOW_RECT, false, 0, nullptr,
-                                        &p->k1b_warps_per_sm)) != cudaSuccess) {
-                        st = fail(KOPEK_ERR_CUDA, "K1W-1024b setup failed: %s", cudaGetErrorString(e));
-                        break;
-                    }
                 }
             }
         }
@@ -640,12 +647,12 @@ static kopek_status stft_launch(const kopek_plan *plan, const float *d_samples, 
         if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "K1M-%u launch failed: %s", plan->n, cudaGetErrorString(e));
         return KOPEK_OK;
     }
-    if (plan->d_k1w && plan->n == 1024 && plan->bins_mode == KOPEK_BINS_HALF && plan->hop % 4 == 0 &&
+    if ((plan->d_k1b || plan->d_k1w) && plan->n == 1024 && plan->bins_mode == KOPEK_BINS_HALF && plan->hop % 4 == 0 &&
         (uintptr_t)d_samples % 16 == 0) {
         K1WParams wp;
         wp.x = d_samples;
         wp.out = d_out;
-        wp.tables = plan->d_k1w;
+        wp.tables = plan->d_k1b;
         wp.n_frames = frames;
         wp.hop = plan->hop;
         wp.pitch = plan->pitch;
@@ -653,9 +660,7 @@ static kopek_status stft_launch(const kopek_plan *plan, const float *d_samples, 
         // bulk-store epilogue: opt-in, f32 spectra, 16-byte aligned rows (else the direct 32-bit stores)
         const bool bulk = plan->bulk_store && plan->output >= KOPEK_OUT_MAG && plan->output <= KOPEK_OUT_DB &&
                           plan->pitch % 4 == 0 && (uintptr_t)d_out % 16 == 0;
-        const int variant = bulk ? 100 : plan->k1w_variant >= 200 ? 0 : plan->k1w_variant;
-        if (plan->d_k1b && plan->k1w_variant >= 200) {
-            wp.tables = plan->d_k1b;
+        if (plan->d_k1b) {
             const uint64_t warps_b = (uint64_t)plan->sm_count * plan->k1b_warps_per_sm;
             const int grid_b = (int)std::min<uint64_t>((frames + 3) / 4, warps_b / 4);
             cudaError_t eb = k1b_launch(wp, (int)plan->output, plan->window != KOPEK_WINDOW_RECT, bulk, grid_b, stream,
@@ -663,6 +668,9 @@ static kopek_status stft_launch(const kopek_plan *plan, const float *d_samples, 
             if (eb != cudaSuccess) return fail(KOPEK_ERR_CUDA, "K1W-1024b launch failed: %s", cudaGetErrorString(eb));
             return KOPEK_OK;
         }
+#ifdef KOPEK_K1W_SWEEP
+        wp.tables = plan->d_k1w;
+        const int variant = bulk ? 100 : plan->k1w_variant;
         const uint64_t warps = (uint64_t)plan->sm_count * plan->k1w_warps_per_sm;
         const int wpb = k1w_variant_warps(variant);
         const int grid = (int)std::min<uint64_t>((frames + wpb - 1) / wpb, warps / wpb);
@@ -670,6 +678,7 @@ static kopek_status stft_launch(const kopek_plan *plan, const float *d_samples, 
                                    nullptr);
         if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "K1W launch failed: %s", cudaGetErrorString(e));
         return KOPEK_OK;
+#endif
     }
     K1Params kp;
     kp.x = d_samples;

@@ -86,9 +86,11 @@ def test_magnitude_power_db(built_lib, oracle_mod, n):
 
 
 @pytest.mark.parametrize("n,hop", [(256, 64), (1024, 256), (2048, 512), (4096, 1024), (512, 130), (1024, 333),
-                                   (256, 1), (1024, 1500)])
+                                   (256, 1), (1024, 1500), (2048, 514), (4096, 1026), (2048, 777), (4096, 5001),
+                                   (4096, 2), (512, 4)])
 def test_hop_addressing(built_lib, oracle_mod, n, hop):
-    """STFT framing is an addressing mode of the load stage; odd hops take the scalar-load path."""
+    """STFT framing is an addressing mode of the load stage; odd hops take the scalar-load path of the generic kernel,
+    hops that are 2 mod 4 the 64-bit loads of the 2048/4096-point team kernel."""
     from kopek_b200 import StftPlan, OUT_MAG, WINDOW_HANN, signals
     x = signals.chirp(n + hop * 45 + 17, 48000.0, 50.0, 15000.0)
     with StftPlan(n, hop, WINDOW_HANN, OUT_MAG) as plan:

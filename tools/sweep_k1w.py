@@ -1,5 +1,10 @@
 #!/usr/bin/env python3
-"""Time every K1W variant (KOPEK_K1W_VARIANT) on the headline shape and check it against K1 (variant -1)."""
+"""Time the 1024-point kernels (KOPEK_K1W_VARIANT) on the headline shape and check them against K1 (variant -1).
+
+Variants 0..13 are the three-pass kernel of fft_warp1024.cuh, which only tuning builds carry:
+    python tools/tune.py build sweep=-DKOPEK_K1W_SWEEP
+    KOPEK_TUNE_TAG=sweep python tools/sweep_k1w.py 1048576 -1,0,200        (200 = the production two-exchange kernel)
+"""
 import os
 import sys
 
