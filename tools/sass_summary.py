@@ -21,7 +21,9 @@ KERNELS = [
     ("K1W-512 |X| Hann", r"k1w_512_kernelILi1ELb1E"),
     ("K1M 2048 dB Hann (configs[1])", r"k1m_kernelILi4ELi3ELi2E"),
     ("K1M 4096 |X| Hann (configs[4])", r"k1m_kernelILi8ELi1ELi2E"),
-    ("K1W three-pass 1024, log bands", r"k1w_1024_kernelILi4ELb1E"),
+    ("K1W-b 1024 log bands Hann", r"k1w_1024b_kernelILi4ELb1ELi4ELi3ELb0E"),
+    ("pcm16 -> f32 (stereo, vector path)", r"pcm16x2_to_f32_kernel"),
+    ("detect_bpm fold (warp per sum)", r"bpm_fold_kernel"),
     ("K2 f64 drop-in, chunk", r"k2_c2c_f64_chunk"),
     ("K3 pass 1, N1 = 4096", r"k3_pass1ILi4096E"),
     ("K3 pass 2, N2 = 4096", r"k3_pass2ILi4096E"),
