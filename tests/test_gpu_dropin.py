@@ -101,3 +101,42 @@ def test_cpp_mirror_harness(built_lib, oracle_mod, tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     assert "DROPIN_OK" in r.stdout and "peak bin 10" in r.stdout
     assert "spectrum\n" in r.stdout          # show() printed the label line
+
+
+def test_fft_and_plans_are_callable_from_many_threads(built_lib, oracle_mod):
+    """kopek::fft::fft is a pure function called from whichever thread owns the UI (egui update, bevy system:
+    SURVEY.md 8b); the drop-in and independent plans must give the same bits when eight threads hammer them at once."""
+    import threading
+
+    import torch
+    from kopek_b200 import fft, StftPlan, OUT_MAG, WINDOW_HANN
+    rng = np.random.default_rng(5)
+    sizes = [1024, 1000, 4096, 257, 1024, 8192, 1024, 64]
+    xs = [rng.standard_normal(n) + 1j * rng.standard_normal(n) for n in sizes]
+    refs = [oracle_mod.fft(x) for x in xs]
+    frames = rng.standard_normal(64 * 1024).astype(np.float32)
+    with StftPlan(1024, 1024, WINDOW_HANN, OUT_MAG) as p0:
+        plan_ref = p0.exec_host(frames)
+    errors = []
+
+    def worker(i):
+        try:
+            torch.cuda.set_device(0)
+            with StftPlan(1024, 1024, WINDOW_HANN, OUT_MAG) as plan:
+                for _ in range(25):
+                    got = fft.fft(xs[i])
+                    if not np.array_equal(_bits(got), _bits(refs[i])):
+                        errors.append(f"thread {i}: fft() bits differ")
+                        return
+                    if not np.array_equal(plan.exec_host(frames), plan_ref):
+                        errors.append(f"thread {i}: plan result differs")
+                        return
+        except Exception as exc:                                    # noqa: BLE001
+            errors.append(f"thread {i}: {exc!r}")
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(len(sizes))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
