@@ -144,7 +144,7 @@ def run_reference(args):
     import oracle
     oracle.build()
     cores = oracle.max_threads()
-    frames = 512 * cores
+    frames = 4096 * cores       # ~0.3 s per step on 16 cores: long enough that thread start-up does not understate the port
     for _ in range(args.warmup):
         cpu_port_rate(min(frames, 64 * cores), cores)
     from kopek_b200 import signals
