@@ -95,6 +95,10 @@ __device__ __forceinline__ float2 mul_w256(float2 v, int m) {
 __device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {      // a * conj(b)
     return make_float2(fmaf(a.y, b.y, a.x * b.x), fmaf(a.y, b.x, -a.x * b.y));
 }
+// multiply by W_4^m = (-i)^m, m a compile-time constant: register renaming and sign flips only
+__device__ __forceinline__ float2 rot_w4(float2 v, int m) {
+    return m == 0 ? v : m == 1 ? make_float2(v.y, -v.x) : m == 2 ? make_float2(-v.x, -v.y) : make_float2(-v.y, v.x);
+}
 __device__ __forceinline__ float2 ldg_stream2(const float2 *p) {
     float2 r;
     asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
@@ -240,12 +244,19 @@ k1m_kernel(const K1WParams p) {
                 g[x] = cmul(recv, tw[x * QD + d]);
             }
             Dft<R>::run(g);
-            zW[d] = g[0];
+            if constexpr (R == 4) {
+                // the phase W_4^{r q} is a quarter turn, and for the READER of this element (r, q) are compile-time
+                // functions of its pair index i (below): stored unphased, rotated for free on the other side
 #pragma unroll
-            for (int q = 1; q < R / 2; ++q) zW[16 * q + d] = cmul(g[q], ph[q]);
-            zW[16 * (R / 2) + d] = make_float2(g[R / 2].x * sgn, g[R / 2].y * sgn);
+                for (int q = 0; q < R; ++q) zW[16 * q + d] = g[q];
+            } else {
+                zW[d] = g[0];
 #pragma unroll
-            for (int q = 1; q < R / 2; ++q) zW[16 * (R / 2 + q) + d] = cmul_conj(g[R / 2 + q], ph[R / 2 - q]);
+                for (int q = 1; q < R / 2; ++q) zW[16 * q + d] = cmul(g[q], ph[q]);
+                zW[16 * (R / 2) + d] = make_float2(g[R / 2].x * sgn, g[R / 2].y * sgn);
+#pragma unroll
+                for (int q = 1; q < R / 2; ++q) zW[16 * (R / 2 + q) + d] = cmul_conj(g[R / 2 + q], ph[R / 2 - q]);
+            }
         }
         if constexpr (T == 32) __syncwarp(); else __syncthreads();
         // ---- split: lane t finishes the pairs (k, M - k), k = t + T i: consecutive lanes, consecutive bins
@@ -254,6 +265,19 @@ k1m_kernel(const K1WParams p) {
         for (int i = 0; i < 8; ++i) {
             a[i] = zA[R * i];
             b[i] = zB[-R * i];
+        }
+        if constexpr (R == 4) {
+            // writer of Z[t + 64 i]: (r, q) = (i % 4, i / 4); of its partner Z[M - k]: (3 - i % 4, 3 - i / 4).  Lane 0
+            // alone pairs inside row 0 one column further (j' -> 64 - j'), which shifts its partners' (r, q).
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                a[i] = rot_w4(a[i], ((i & 3) * (i >> 2)) & 3);
+                b[i] = rot_w4(b[i], ((3 - (i & 3)) * (3 - (i >> 2))) & 3);
+            }
+            if (t == 0) {
+#pragma unroll
+                for (int i = 1; i < 8; ++i) b[i] = rot_w4(b[i], i < 4 ? 3 : 2);
+            }
         }
         if (t == 0) b[0] = a[0];                             // k = 0 pairs with itself (Z[M] = Z[0])
         constexpr int EB = OUT == OUT_COMPLEX ? 8 : 4;
