@@ -174,6 +174,10 @@ KOPEK_API kopek_status kopek_pcm16_to_f32(const int16_t *d_pcm, uint64_t n_frame
 KOPEK_API kopek_status kopek_detect_bpm(const int16_t *d_frames, uint64_t n_frames, float sample_rate, uint32_t *bpm_out,
                                         uint32_t *beats_out, float *d_block_e, float *d_avg_e, int device,
                                         void *cuda_stream);
+/* the drop-in shape of detect_bpm(frames: Vec<[i16; 2]>, sample_rate: f32) -> u32: HOST frames; the duration * 44100
+ * frames the algorithm reads are staged to the device, the rest as above */
+KOPEK_API kopek_status kopek_detect_bpm_host(const int16_t *h_frames, uint64_t n_frames, float sample_rate,
+                                             uint32_t *bpm_out, uint32_t *beats_out, int device);
 
 /* ---- 2d. peer-direct spectrogram (multi-GPU, one process per GPU) -------------------------------
  * When the caller wants ONE spectrogram on one GPU, the other ranks do not send their spectra after

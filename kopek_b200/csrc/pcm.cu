@@ -209,3 +209,35 @@ extern "C" kopek_status kopek_detect_bpm(const int16_t *d_frames, uint64_t n_fra
     *bpm_out = beats * (60u / (uint32_t)duration);                                          // decoder.rs:70, u32 division
     return KOPEK_OK;
 }
+
+// host-buffer form: the exact shape of kopek::decoder::detect_bpm(frames: Vec<[i16; 2]>, sample_rate: f32) -> u32
+extern "C" kopek_status kopek_detect_bpm_host(const int16_t *h_frames, uint64_t n_frames, float sample_rate,
+                                              uint32_t *bpm_out, uint32_t *beats_out, int device) {
+    if (!h_frames || !bpm_out) return fail(KOPEK_ERR_INVALID, "NULL argument");
+    if (!(sample_rate > 0.0f)) return fail(KOPEK_ERR_INVALID, "sample_rate must be positive");
+    const uint64_t duration = (uint64_t)((float)n_frames / sample_rate);
+    if (duration == 0) return fail(KOPEK_ERR_INVALID, "detect_bpm: less than one second of audio (the reference divides by zero)");
+    if (duration * 44100 > n_frames)
+        return fail(KOPEK_ERR_INVALID, "detect_bpm: %llu seconds x 44100 frames exceed the %llu frames given (the reference "
+                    "indexes out of bounds)", (unsigned long long)duration, (unsigned long long)n_frames);
+    DeviceGuard g(device);
+    if (!g.ok) return fail(KOPEK_ERR_CUDA, "cannot select device %d", device);
+    cudaMemPool_t pool = scratch_pool(device);
+    if (!pool) return fail(KOPEK_ERR_CUDA, "detect_bpm: cannot create the scratch pool: %s", cudaGetErrorString(cudaGetLastError()));
+    // only the frames the algorithm reads (duration * 44100) cross PCIe
+    const uint64_t used = duration * 44100;
+    cudaStream_t st = nullptr;
+    KOPEK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    int16_t *d_frames = nullptr;
+    cudaError_t e = cudaMallocFromPoolAsync(&d_frames, used * 4, pool, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_frames, h_frames, used * 4, cudaMemcpyHostToDevice, st);
+    kopek_status rc = KOPEK_OK;
+    if (e != cudaSuccess) rc = fail(KOPEK_ERR_CUDA, "detect_bpm: staging the frames failed: %s", cudaGetErrorString(e));
+    // same (n_frames, sample_rate) as given, so the duration is computed from the same f32 quotient; the device
+    // routine reads the first duration * 44100 frames only
+    else rc = kopek_detect_bpm(d_frames, n_frames, sample_rate, bpm_out, beats_out, nullptr, nullptr, device, st);
+    if (d_frames) cudaFreeAsync(d_frames, st);
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+    return rc;
+}

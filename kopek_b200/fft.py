@@ -86,6 +86,14 @@ def detect_bpm_device(d_frames: int, n_frames: int, sample_rate: float = 44100.0
     return int(bpm.value), int(beats.value)
 
 
+def detect_bpm(frames, sample_rate: float = 44100.0, device: int = 0):
+    """kopek::decoder::detect_bpm(frames: Vec<[i16; 2]>, sample_rate) -- host frames in, (bpm, beats) out."""
+    f = np.ascontiguousarray(frames, dtype=np.int16).reshape(-1, 2)
+    bpm, beats = C.c_uint32(0), C.c_uint32(0)
+    check(_lib.load().kopek_detect_bpm_host(f.ctypes.data, f.shape[0], sample_rate, C.byref(bpm), C.byref(beats), device))
+    return int(bpm.value), int(beats.value)
+
+
 def show_format(label: str, buf) -> str:
     a = np.ascontiguousarray(buf, dtype=np.complex128).reshape(-1)
     lib = _lib.load()

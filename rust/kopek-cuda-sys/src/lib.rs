@@ -79,6 +79,8 @@ extern "C" {
     pub fn kopek_detect_bpm(d_frames: *const i16, n_frames: u64, sample_rate: f32, bpm_out: *mut u32,
                             beats_out: *mut u32, d_block_e: *mut f32, d_avg_e: *mut f32, device: c_int,
                             cuda_stream: *mut c_void) -> kopek_status;
+    pub fn kopek_detect_bpm_host(h_frames: *const i16, n_frames: u64, sample_rate: f32, bpm_out: *mut u32,
+                                 beats_out: *mut u32, device: c_int) -> kopek_status;
     pub fn kopek_device_alloc(d_ptr: *mut *mut c_void, bytes: usize, device: c_int) -> kopek_status;
     pub fn kopek_device_free(d_ptr: *mut c_void, device: c_int) -> kopek_status;
     pub fn kopek_copy(dst: *mut c_void, src: *const c_void, bytes: usize, device: c_int) -> kopek_status;

@@ -1,1 +1,2 @@
+pub mod decoder;
 pub mod fft;

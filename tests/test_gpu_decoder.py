@@ -80,3 +80,14 @@ def test_decoded_frames_to_spectrum(built_lib, oracle_mod):
     ref = np.stack([oracle_mod.mag_norm(oracle_mod.fft(oracle_mod.marshal(x[f * n:(f + 1) * n, 0].astype(np.float32), 32767.0)))
                     [: n // 2 + 1] for f in range(frames)])
     assert frame_rel_err(out.cpu().numpy().astype(np.float64), ref) <= tol(n)
+
+
+def test_detect_bpm_host_entry_point(built_lib, oracle_mod):
+    """kopek_detect_bpm_host: the drop-in shape of detect_bpm(frames: Vec<[i16; 2]>, sample_rate) -> u32."""
+    from kopek_b200 import fft, KopekError
+    for seconds, bpm, seed in ((2.82, 83, 11), (9.3, 140, 12), (400.0, 120, 13)):
+        x = _click_track(seconds, bpm, seed)
+        ref_bpm, ref_beats, _, _ = oracle_mod.detect_bpm(x)
+        assert fft.detect_bpm(x) == (ref_bpm, ref_beats)
+    with pytest.raises(KopekError):
+        fft.detect_bpm(_click_track(0.3, 120, 14)[:10000])
