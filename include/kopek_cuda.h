@@ -179,6 +179,14 @@ KOPEK_API kopek_status kopek_detect_bpm(const int16_t *d_frames, uint64_t n_fram
 KOPEK_API kopek_status kopek_detect_bpm_host(const int16_t *h_frames, uint64_t n_frames, float sample_rate,
                                              uint32_t *bpm_out, uint32_t *beats_out, int device);
 
+/* kopek_stft_exec_pcm16: kopek_stft_exec on decoded audio -- n_frames interleaved STEREO i16 frames, sample =
+ * frame[channel] as f64 / i16::MAX (examples/graph/player.rs:56-59); hop and n count frames.  For n = 1024 plans
+ * (HALF bins, hop % 4 == 0, 16-byte aligned frames) the marshalling is fused into the kernel's load stage: one
+ * pass from PCM to spectrum, results bit-identical to kopek_pcm16_to_f32 followed by kopek_stft_exec; other plans
+ * take exactly that two-step route through a stream-ordered scratch buffer. */
+KOPEK_API kopek_status kopek_stft_exec_pcm16(const kopek_plan *plan, const int16_t *d_frames, uint64_t n_frames,
+                                             uint32_t channel, void *d_out, uint64_t *n_frames_out, void *cuda_stream);
+
 /* ---- 2d. peer-direct spectrogram (multi-GPU, one process per GPU) -------------------------------
  * When the caller wants ONE spectrogram on one GPU, the other ranks do not send their spectra after
  * the fact: they run kopek_stft_exec with d_out pointing INTO the owner's buffer, mapped through CUDA

@@ -43,6 +43,7 @@ SYMBOLS = {
     "kopek_plan_out_elem_bytes": (_u64, [_vp]),
     "kopek_plan_last_launches": (_u32, [_vp]),
     "kopek_stft_exec": (_i32, [_vp, _vp, _u64, _vp, C.POINTER(_u64), _vp]),
+    "kopek_stft_exec_pcm16": (_i32, [_vp, _vp, _u64, _u32, _vp, C.POINTER(_u64), _vp]),
     "kopek_stft_exec_host": (_i32, [_vp, _vp, _u64, _vp, C.POINTER(_u64)]),
     "kopek_stream_create": (_i32, [C.POINTER(_vp), _u32, _u32, _u32, C.c_float, C.c_int]),
     "kopek_stream_push": (_i32, [_vp, _vp, _u32, _vp]),

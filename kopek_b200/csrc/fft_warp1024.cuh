@@ -33,6 +33,7 @@ struct K1WParams {
     uint64_t hop;
     uint64_t pitch;
     float band_scale;        // OUT_BANDS_*: display scale applied to the band means
+    uint32_t pcm_shift;      // PCM input (fft_warp1024b.cuh): 16 = channel 0 (low half of a stereo frame), 0 = channel 1
 };
 
 constexpr int K1W_WIN_F4 = 256;            // 0.5 * w[4i .. 4i+3]

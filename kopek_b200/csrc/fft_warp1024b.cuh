@@ -40,7 +40,19 @@ __device__ __forceinline__ uint32_t k1b_smem_u32(const void *ptr) {
 // BULK (f32 outputs, rows 16-byte aligned: pitch % 4 == 0): the 513 values of a frame are staged in shared memory
 // and leave as ONE cp.async.bulk store of 2048 bytes (+ bin 512) -- the form that reaches link bandwidth when
 // p.out is a peer GPU's memory (kopek_plan_set_bulk_store).
-template <int OUT, bool WIN, int WARPS, int MINB, bool BULK = false>
+// PCM: p.x points at interleaved STEREO i16 frames (kopek::decoder::decode, src/decoder.rs:1-31) and hop counts frames;
+// the marshalling of examples/graph/player.rs:56-59 -- frame[channel] as f64 / i16::MAX, narrowed once to f32 -- is
+// fused into the load stage, so decoded audio reaches its spectrum in one pass (4 bytes in per sample, like f32 mono).
+// s / 32767 is evaluated as q = s r, q += fma(-q, 32767, s) r with r = RN(1/32767): for all 65536 inputs this equals
+// the f64 quotient narrowed to f32 (tests/test_oracle.py::test_pcm16_marshalling checks the identity exhaustively).
+__device__ __forceinline__ float pcm16_sample(float raw_bits, uint32_t shift) {
+    const float sf = (float)((__float_as_int(raw_bits) << shift) >> 16);
+    constexpr float r = 1.0f / 32767.0f;
+    const float q = sf * r;
+    return fmaf(fmaf(-q, 32767.0f, sf), r, q);
+}
+
+template <int OUT, bool WIN, int WARPS, int MINB, bool BULK = false, bool PCM = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 k1w_1024b_kernel(const K1WParams p) {
     constexpr int M = 512;
@@ -84,8 +96,10 @@ k1w_1024b_kernel(const K1WParams p) {
         float2 e[16];
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) {
-            if constexpr (WIN) e[n1] = make_float2(vn[n1].x * rw[n1].x, vn[n1].y * rw[n1].y);
-            else e[n1] = vn[n1];
+            float2 v = vn[n1];
+            if constexpr (PCM) v = make_float2(pcm16_sample(v.x, p.pcm_shift), pcm16_sample(v.y, p.pcm_shift));
+            if constexpr (WIN) e[n1] = make_float2(v.x * rw[n1].x, v.y * rw[n1].y);
+            else e[n1] = v;
         }
         if (frame + total_warps < p.n_frames) load_frame(frame + total_warps, vn);
 

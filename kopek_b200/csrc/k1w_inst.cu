@@ -142,10 +142,10 @@ void k1b_build_tables(const float *half_window /* 1024 or nullptr */, float4 *ou
     }
 }
 
-template <int OUT, bool WIN, bool BULK = false>
+template <int OUT, bool WIN, bool BULK = false, bool PCM = false>
 static cudaError_t launch1b(const K1WParams &p, int grid, cudaStream_t stream, int *occ_out) {
     constexpr int WARPS = 4;
-    auto kern = k1w_1024b_kernel<OUT, WIN, WARPS, 3, BULK>;
+    auto kern = k1w_1024b_kernel<OUT, WIN, WARPS, 3, BULK, PCM>;
     constexpr size_t smem = sizeof(float2) * WARPS * (K1B_EX_F2 + (BULK ? K1B_STAGE_F2 : 0));
     if (occ_out) {
         int nb = 0;
@@ -155,6 +155,24 @@ static cudaError_t launch1b(const K1WParams &p, int grid, cudaStream_t stream, i
     }
     kern<<<grid, WARPS * 32, smem, stream>>>(p);
     return cudaGetLastError();
+}
+
+cudaError_t k1b_launch_pcm(const K1WParams &p, int output, bool win, int grid, cudaStream_t stream) {
+    switch (output * 2 + (win ? 1 : 0)) {
+        case 0: return launch1b<OUT_COMPLEX, false, false, true>(p, grid, stream, nullptr);
+        case 1: return launch1b<OUT_COMPLEX, true, false, true>(p, grid, stream, nullptr);
+        case 2: return launch1b<OUT_MAG, false, false, true>(p, grid, stream, nullptr);
+        case 3: return launch1b<OUT_MAG, true, false, true>(p, grid, stream, nullptr);
+        case 4: return launch1b<OUT_POWER, false, false, true>(p, grid, stream, nullptr);
+        case 5: return launch1b<OUT_POWER, true, false, true>(p, grid, stream, nullptr);
+        case 6: return launch1b<OUT_DB, false, false, true>(p, grid, stream, nullptr);
+        case 7: return launch1b<OUT_DB, true, false, true>(p, grid, stream, nullptr);
+        case 8: return launch1b<OUT_BANDS_LOG, false, false, true>(p, grid, stream, nullptr);
+        case 9: return launch1b<OUT_BANDS_LOG, true, false, true>(p, grid, stream, nullptr);
+        case 10: return launch1b<OUT_BANDS_LOW, false, false, true>(p, grid, stream, nullptr);
+        case 11: return launch1b<OUT_BANDS_LOW, true, false, true>(p, grid, stream, nullptr);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 cudaError_t k1b_launch(const K1WParams &p, int output, bool win, bool bulk, int grid, cudaStream_t stream,

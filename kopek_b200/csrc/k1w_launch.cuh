@@ -15,6 +15,8 @@ constexpr int K1B_TABLE_F4 = (512 + 480 + 16 + 32) / 2;
 void k1b_build_tables(const float *half_window, float4 *out /* K1B_TABLE_F4 */);
 cudaError_t k1b_launch(const K1WParams &p, int output, bool win, bool bulk, int grid, cudaStream_t stream,
                        int *occ_out);
+// same kernel reading interleaved stereo i16 frames (p.x, p.hop in frames, p.pcm_shift selects the channel)
+cudaError_t k1b_launch_pcm(const K1WParams &p, int output, bool win, int grid, cudaStream_t stream);
 
 // 256-point kernel, eight lanes per frame (fft_warp256.cuh): 4 warps per CTA, 4 frames per warp
 constexpr int K1W256_TABLE_F4 = 64 + 56 + 8;

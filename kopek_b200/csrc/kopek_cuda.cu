@@ -615,7 +615,7 @@ static kopek_status stft_launch(const kopek_plan *plan, const float *d_samples, 
         return fail(KOPEK_ERR_INVALID, "band epilogues need a 16-byte aligned sample buffer");
     if (plan->d_k1w && (plan->n == 256 || plan->n == 512) && plan->bins_mode == KOPEK_BINS_HALF && plan->hop % 4 == 0 &&
         (uintptr_t)d_samples % 16 == 0) {
-        K1WParams wp;
+        K1WParams wp{};
         wp.x = d_samples;
         wp.out = d_out;
         wp.tables = plan->d_k1w;
@@ -634,7 +634,7 @@ static kopek_status stft_launch(const kopek_plan *plan, const float *d_samples, 
         return KOPEK_OK;
     }
     if (plan->d_k1m && plan->bins_mode == KOPEK_BINS_HALF && plan->hop % 2 == 0 && (uintptr_t)d_samples % 8 == 0) {
-        K1WParams wp;
+        K1WParams wp{};
         wp.x = d_samples;
         wp.out = d_out;
         wp.tables = plan->d_k1m;
@@ -649,7 +649,7 @@ static kopek_status stft_launch(const kopek_plan *plan, const float *d_samples, 
     }
     if ((plan->d_k1b || plan->d_k1w) && plan->n == 1024 && plan->bins_mode == KOPEK_BINS_HALF && plan->hop % 4 == 0 &&
         (uintptr_t)d_samples % 16 == 0) {
-        K1WParams wp;
+        K1WParams wp{};
         wp.x = d_samples;
         wp.out = d_out;
         wp.tables = plan->d_k1b;
@@ -715,6 +715,53 @@ kopek_status kopek_stft_exec(const kopek_plan *plan, const float *d_samples, uin
     if (!g.ok) return fail(KOPEK_ERR_CUDA, "cannot select device %d", plan->device);
     kopek_status st = stft_launch(plan, d_samples, frames, d_out, (cudaStream_t)cuda_stream);
     if (st == KOPEK_OK) plan->last_launches = 1;
+    return st;
+}
+
+// decoded PCM in, spectra out: interleaved stereo i16 frames -> frame[channel] / i16::MAX -> plan.
+// n = 1024 (the frame size of the reference's callers) fuses the marshalling into the kernel's load stage; other
+// geometries convert into a stream-ordered scratch buffer first (kopek_pcm16_to_f32) and run the plan on it.
+kopek_status kopek_stft_exec_pcm16(const kopek_plan *plan, const int16_t *d_frames, uint64_t n_frames, uint32_t channel,
+                                   void *d_out, uint64_t *n_frames_out, void *cuda_stream) {
+    if (!plan) return fail(KOPEK_ERR_INVALID, "plan is NULL");
+    const uint64_t frames = kopek_plan_frames(plan, n_frames);       // one sample per PCM frame
+    if (n_frames_out) *n_frames_out = frames;
+    plan->last_launches = 0;
+    if (frames == 0) return KOPEK_OK;
+    if (!d_frames || !d_out) return fail(KOPEK_ERR_INVALID, "NULL device pointer");
+    if (channel > 1) return fail(KOPEK_ERR_INVALID, "channel %u of a stereo frame", channel);
+    if ((uintptr_t)d_frames % 4 != 0 || (uintptr_t)d_out % plan->elem_bytes != 0)
+        return fail(KOPEK_ERR_INVALID, "misaligned device pointer");
+    DeviceGuard g(plan->device);
+    if (!g.ok) return fail(KOPEK_ERR_CUDA, "cannot select device %d", plan->device);
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    if (plan->d_k1b && plan->n == 1024 && plan->bins_mode == KOPEK_BINS_HALF && plan->hop % 4 == 0 &&
+        (uintptr_t)d_frames % 16 == 0) {
+        K1WParams wp{};
+        wp.x = reinterpret_cast<const float *>(d_frames);              // one 32-bit word per stereo frame
+        wp.out = d_out;
+        wp.tables = plan->d_k1b;
+        wp.n_frames = frames;
+        wp.hop = plan->hop;
+        wp.pitch = plan->pitch;
+        wp.band_scale = plan->band_scale;
+        wp.pcm_shift = channel ? 0u : 16u;
+        const uint64_t warps_b = (uint64_t)plan->sm_count * plan->k1b_warps_per_sm;
+        const int grid_b = (int)std::min<uint64_t>((frames + 3) / 4, warps_b / 4);
+        cudaError_t e = k1b_launch_pcm(wp, (int)plan->output, plan->window != KOPEK_WINDOW_RECT, grid_b, stream);
+        if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "K1W-1024b (PCM) launch failed: %s", cudaGetErrorString(e));
+        plan->last_launches = 1;
+        return KOPEK_OK;
+    }
+    const uint64_t n_used = (frames - 1) * plan->hop + plan->n;
+    float *scratch = nullptr;
+    cudaError_t e = cudaMallocAsync(&scratch, n_used * sizeof(float), stream);
+    if (e != cudaSuccess) return fail(KOPEK_ERR_NOMEM, "PCM scratch of %llu samples: %s", (unsigned long long)n_used,
+                                      cudaGetErrorString(e));
+    kopek_status st = kopek_pcm16_to_f32(d_frames, n_used, 2, channel, 32767.0, scratch, plan->device, cuda_stream);
+    if (st == KOPEK_OK) st = stft_launch(plan, scratch, frames, d_out, stream);
+    cudaFreeAsync(scratch, stream);
+    if (st == KOPEK_OK) plan->last_launches = 2;
     return st;
 }
 

@@ -150,6 +150,12 @@ class StftPlan:
         check(self._lib.kopek_stft_exec(self._h, d_samples, n_samples, d_out, C.byref(nf), stream or None))
         return nf.value
 
+    def exec_pcm16_ptr(self, d_frames: int, n_frames: int, d_out: int, channel: int = 0, stream: int = 0) -> int:
+        """Interleaved stereo i16 frames (device) in: frame[channel] / i16::MAX feeds the plan (fused for n = 1024)."""
+        nf = C.c_uint64(0)
+        check(self._lib.kopek_stft_exec_pcm16(self._h, d_frames, n_frames, channel, d_out, C.byref(nf), stream or None))
+        return nf.value
+
     def exec_host_ptr(self, h_samples: int, n_samples: int, h_out: int) -> int:
         nf = C.c_uint64(0)
         check(self._lib.kopek_stft_exec_host(self._h, h_samples, n_samples, h_out, C.byref(nf)))

@@ -74,6 +74,8 @@ extern "C" {
     pub fn kopek_synth_frames(d_out: *mut f32, n_frames: u64, n: u32, stride: u64, sample_rate: f32, wave: u32,
                               duty: f32, freq0: f32, freq_step: f32, freq_mod: u32, noise: u32, noise_gain: f32,
                               seed: u64, first_frame: u64, device: c_int, cuda_stream: *mut c_void) -> kopek_status;
+    pub fn kopek_stft_exec_pcm16(plan: *const kopek_plan, d_frames: *const i16, n_frames: u64, channel: u32,
+                                 d_out: *mut c_void, n_frames_out: *mut u64, cuda_stream: *mut c_void) -> kopek_status;
     pub fn kopek_pcm16_to_f32(d_pcm: *const i16, n_frames: u64, channels: u32, channel: u32, divisor: f64,
                               d_out: *mut f32, device: c_int, cuda_stream: *mut c_void) -> kopek_status;
     pub fn kopek_detect_bpm(d_frames: *const i16, n_frames: u64, sample_rate: f32, bpm_out: *mut u32,

@@ -91,3 +91,36 @@ def test_detect_bpm_host_entry_point(built_lib, oracle_mod):
         assert fft.detect_bpm(x) == (ref_bpm, ref_beats)
     with pytest.raises(KopekError):
         fft.detect_bpm(_click_track(0.3, 120, 14)[:10000])
+
+
+@pytest.mark.parametrize("n,hop,output,window", [(1024, 1024, 1, 0), (1024, 256, 3, 1), (1024, 1024, 0, 2), (1024, 512, 2, 1),
+                                                 (1024, 1024, 4, 0), (1024, 1024, 5, 1), (2048, 512, 1, 1),
+                                                 (1024, 333, 1, 1), (256, 256, 1, 0), (4096, 4096, 3, 2)])
+def test_pcm16_frames_straight_into_the_plan(built_lib, oracle_mod, n, hop, output, window):
+    """kopek_stft_exec_pcm16: fused marshalling (n = 1024) or conversion + plan (elsewhere) -- bit-identical to
+    kopek_pcm16_to_f32 followed by kopek_stft_exec, and within tolerance of the f64 oracle on the marshalled samples."""
+    import torch
+    from kopek_b200 import fft, StftPlan
+    frames = 301
+    n_frames = (frames - 1) * hop + n + 5
+    x = _click_track(n_frames / 44100.0 + 0.1, 150, n + hop)[:n_frames]
+    x[:4, 0] = [32767, -32768, 0, -1]
+    x[:4, 1] = [-32768, 32767, 1, 0]
+    d = torch.from_numpy(x).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    for channel in (0, 1):
+        with StftPlan(n, hop, window, output) as plan:
+            dt = torch.complex64 if output == 0 else torch.float32
+            a = torch.full((frames, plan.pitch), float("nan"), device="cuda", dtype=dt)
+            b = torch.full((frames, plan.pitch), float("nan"), device="cuda", dtype=dt)
+            assert plan.exec_pcm16_ptr(d.data_ptr(), n_frames, a.data_ptr(), channel, st) == frames
+            assert plan.last_launches == (1 if n == 1024 and hop % 4 == 0 else 2)
+            samples = torch.empty(n_frames, device="cuda")
+            fft.pcm16_to_f32_device(d.data_ptr(), n_frames, samples.data_ptr(), 2, channel)
+            assert plan.exec_ptr(samples.data_ptr(), n_frames, b.data_ptr(), st) == frames
+            torch.cuda.synchronize()
+            ra, rb = (torch.view_as_real(a), torch.view_as_real(b)) if output == 0 else (a, b)
+            assert torch.equal(ra, rb)
+            if output == 1:
+                ref = oracle_mod.stft_mag(oracle_mod.pcm16_to_f32(x, channel), n, hop, window)
+                assert (np.abs(a.cpu().numpy() - ref) / ref.max(axis=1, keepdims=True)).max() <= tol(n)

@@ -197,3 +197,14 @@ def test_pcm16_marshalling(oracle_mod):
         ref = (pcm[:, ch].astype(np.float64) / 32767.0).astype(np.float32)
         np.testing.assert_array_equal(got, ref)
     assert oracle_mod.pcm16_to_f32(pcm, 0)[0] == 1.0
+    # the identity the fused load stage of fft_warp1024b.cuh relies on, for ALL 65536 inputs:
+    # q = s r, q += fma(-q, 32767, s) r with r = RN(1/32767)  ==  (f32)((f64)s / 32767)   (and so is a plain f32 division)
+    s_all = np.arange(-32768, 32768, dtype=np.int16)
+    ref = oracle_mod.pcm16_to_f32(s_all)
+    sf = s_all.astype(np.float32)
+    r = np.float32(1.0) / np.float32(32767.0)
+    q0 = (sf * r).astype(np.float32)
+    e = (sf.astype(np.float64) - q0.astype(np.float64) * 32767.0).astype(np.float32)      # fma: one rounding
+    q1 = (e.astype(np.float64) * np.float64(r) + q0.astype(np.float64)).astype(np.float32)
+    np.testing.assert_array_equal(q1, ref)
+    np.testing.assert_array_equal((sf / np.float32(32767.0)).astype(np.float32), ref)

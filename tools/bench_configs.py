@@ -92,6 +92,13 @@ o32 = torch.empty(nfr, device="cuda")
 ms = timed(lambda: fft.pcm16_to_f32_device(pcm.data_ptr(), nfr, o32.data_ptr(), 2, 0, stream=st), iters=10)
 dec_rows.append((f"pcm16 -> f32, channel 0 / 32767 (f64 division), 2^28 stereo frames", ms, nfr * 8))
 del o32
+pl = StftPlan(1024, 1024, WINDOW_HANN, OUT_MAG)
+fr = nfr // 1024
+spec = torch.empty((fr, pl.pitch), device="cuda")
+ms = timed(lambda: pl.exec_pcm16_ptr(pcm.data_ptr(), nfr, spec.data_ptr(), 0, st), iters=10)
+dec_rows.append((f"pcm16 stereo -> Hann 1024 |X| fused (kopek_stft_exec_pcm16), 2^18 frames", ms, nfr * 4 + fr * 513 * 4))
+pl.close()
+del spec
 hour = 3600 * 44100
 ms = timed(lambda: fft.detect_bpm_device(pcm.data_ptr(), hour, 44100.0, stream=st), iters=5, warm=1)
 dec_rows.append((f"detect_bpm, 1 h of 44.1 kHz stereo (sequential f32 folds, bit-exact)", ms, hour * 4))
