@@ -81,6 +81,9 @@ KOPEK_API size_t kopek_next_pow2(size_t n);
 KOPEK_API kopek_status kopek_fft_c2c_f64(const double *in, size_t n_in, double *out, size_t n_out);
 /* `batch` independent transforms of n_in points each, laid out back to back
  * (input stride n_in, output stride kopek_next_pow2(n_in) complex values). */
+/* Inverse of the above through the forward transform, x = conj(fft(conj(X))) / n (the reference has no inverse:
+ * this is the one a caller of its fft() would write).  n must be a power of two; host pointers. */
+KOPEK_API kopek_status kopek_ifft_c2c_f64(const double *in, size_t n, double *out);
 KOPEK_API kopek_status kopek_fft_c2c_f64_batched(const double *in, size_t n_in, size_t batch, double *out);
 /* Same, device-resident buffers, asynchronous on `cuda_stream` (a cudaStream_t; NULL = default). */
 KOPEK_API kopek_status kopek_fft_c2c_f64_device(const double *d_in, size_t n_in, size_t batch, double *d_out,

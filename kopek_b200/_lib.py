@@ -28,6 +28,7 @@ SYMBOLS = {
     "kopek_device_count": (_i32, []),
     "kopek_next_pow2": (_sz, [_sz]),
     "kopek_fft_c2c_f64": (_i32, [_vp, _sz, _vp, _sz]),
+    "kopek_ifft_c2c_f64": (_i32, [_vp, _sz, _vp]),
     "kopek_fft_c2c_f64_batched": (_i32, [_vp, _sz, _sz, _vp]),
     "kopek_fft_c2c_f64_device": (_i32, [_vp, _sz, _sz, _vp, C.c_int, _vp]),
     "kopek_show_format": (_sz, [C.c_char_p, _vp, _sz, _vp, _sz]),

@@ -336,6 +336,22 @@ kopek_status kopek_fft_c2c_f64(const double *in, size_t n_in, double *out, size_
     return k2_run_host(in, n_in, 1, out);
 }
 
+// Inverse through the forward transform: x = conj(fft(conj(X))) / n.  The reference has no inverse (SURVEY.md 8f row
+// 4); this is the one a caller of its fft() would write, and it makes fft -> ifft round trips a property test of the
+// forward path at any size.  n must be a power of two (an inverse cannot zero-pad); 1/n is exact.
+kopek_status kopek_ifft_c2c_f64(const double *in, size_t n, double *out) {
+    if (n == 0 || (n & (n - 1))) return fail(KOPEK_ERR_INVALID, "inverse transform: n=%zu must be a power of two >= 1", n);
+    if (!in || !out) return fail(KOPEK_ERR_INVALID, "NULL argument");
+    std::vector<double> tmp;
+    try { tmp.resize(2 * n); } catch (...) { return fail(KOPEK_ERR_NOMEM, "out of host memory"); }
+    for (size_t i = 0; i < n; ++i) { tmp[2 * i] = in[2 * i]; tmp[2 * i + 1] = -in[2 * i + 1]; }
+    kopek_status st = k2_run_host(tmp.data(), n, 1, out);
+    if (st != KOPEK_OK) return st;
+    const double inv = 1.0 / (double)n;
+    for (size_t i = 0; i < n; ++i) { out[2 * i] = out[2 * i] * inv; out[2 * i + 1] = -out[2 * i + 1] * inv; }
+    return KOPEK_OK;
+}
+
 kopek_status kopek_fft_c2c_f64_batched(const double *in, size_t n_in, size_t batch, double *out) {
     return k2_run_host(in, n_in, batch, out);
 }

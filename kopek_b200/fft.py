@@ -70,6 +70,14 @@ def synth_frames_device(d_out: int, n_frames: int, n: int, sample_rate: float, w
                                          stream or None))
 
 
+def ifft(spectrum) -> np.ndarray:
+    """Inverse through the forward drop-in: conj(fft(conj(X))) / n, n a power of two (kopek_ifft_c2c_f64)."""
+    a = np.ascontiguousarray(spectrum, dtype=np.complex128).reshape(-1)
+    out = np.empty(a.size, dtype=np.complex128)
+    check(_lib.load().kopek_ifft_c2c_f64(a.ctypes.data, a.size, out.ctypes.data))
+    return out
+
+
 def pcm16_to_f32_device(d_pcm: int, n_frames: int, d_out: int, channels: int = 2, channel: int = 0,
                         divisor: float = 32767.0, device: int = 0, stream: int = 0) -> None:
     """kopek_pcm16_to_f32: frame[channel] as f64 / i16::MAX (examples/graph/player.rs:56-59), device pointers."""

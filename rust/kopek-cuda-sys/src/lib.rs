@@ -44,6 +44,7 @@ extern "C" {
     pub fn kopek_next_pow2(n: usize) -> usize;
     /// `in_`/`out`: interleaved (re, im) f64 == `*const Complex<f64>` (num-complex is #[repr(C)]).
     pub fn kopek_fft_c2c_f64(in_: *const f64, n_in: usize, out: *mut f64, n_out: usize) -> kopek_status;
+    pub fn kopek_ifft_c2c_f64(in_: *const f64, n: usize, out: *mut f64) -> kopek_status;
     pub fn kopek_fft_c2c_f64_batched(in_: *const f64, n_in: usize, batch: usize, out: *mut f64) -> kopek_status;
     pub fn kopek_fft_c2c_f64_device(d_in: *const f64, n_in: usize, batch: usize, d_out: *mut f64, device: c_int,
                                     cuda_stream: *mut c_void) -> kopek_status;

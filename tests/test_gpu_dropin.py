@@ -140,3 +140,20 @@ def test_fft_and_plans_are_callable_from_many_threads(built_lib, oracle_mod):
     for t in ts:
         t.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("n", [1, 2, 8, 1024, 4096, 1 << 16, 1 << 20])
+def test_inverse_round_trip(built_lib, oracle_mod, n):
+    """fft -> ifft is the identity: a size-independent property of the forward path, and the inverse itself equals
+    the composition conj(oracle.fft(conj(X))) / n bit for bit."""
+    from kopek_b200 import fft, KopekError
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    X = fft.fft(x)
+    back = fft.ifft(X)
+    assert np.abs(back - x).max() <= 1e-13 * max(1.0, np.log2(n)) * np.abs(x).max()
+    ref = np.conj(oracle_mod.fft(np.conj(X))) / n
+    np.testing.assert_array_equal(_bits(back), _bits(ref))
+    if n == 8:
+        with pytest.raises(KopekError):
+            fft.ifft(X[:6])                       # an inverse cannot zero-pad
