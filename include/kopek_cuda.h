@@ -211,6 +211,16 @@ KOPEK_API kopek_status kopek_ipc_close(void *d_ptr, int device);
 KOPEK_API kopek_status kopek_fft_large_c2c_f32(const float *d_in, float *d_out, uint64_t n, int device,
                                                void *cuda_stream);
 
+/* ---- 2e. one large transform over R GPUs (one process per GPU) -----------------------------------------
+ * n = R * local_n points; rank r holds the cyclic slice x[j R + r].  Each rank runs kopek_fft_large_c2c_f32 on its
+ * slice (F_r, local_n complex f32), the ranks exchange CUDA-IPC handles of those buffers (2d) and, after a barrier,
+ * each calls kopek_fft_dist_combine: ONE kernel that reads F_r[k'] of every rank over NVLink for the k' of this
+ * rank's block [rank * local_n / R, ...), applies W_n^{r k'} and the radix-R butterfly across the ranks, and writes
+ * d_out[q][i] = X[(rank * local_n / R + i) + local_n * q]  (R rows of local_n / R complex).  d_spectra is a HOST
+ * array of R device pointers (entry `rank` = this rank's own buffer, the others peer mappings); R = 2, 4 or 8. */
+KOPEK_API kopek_status kopek_fft_dist_combine(const float *const *d_spectra, uint32_t ranks, uint32_t rank,
+                                              uint64_t local_n, float *d_out, int device, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,7 @@ SYMBOLS = {
     "kopek_ipc_export": (_i32, [_vp, _vp]),
     "kopek_ipc_open": (_i32, [_vp, C.c_int, C.POINTER(_vp)]),
     "kopek_ipc_close": (_i32, [_vp, C.c_int]),
+    "kopek_fft_dist_combine": (_i32, [_vp, _u32, _u32, _u64, _vp, C.c_int, _vp]),
     "kopek_host_alloc": (_i32, [C.POINTER(_vp), _sz]),
     "kopek_host_free": (_i32, [_vp]),
     "kopek_fft_large_c2c_f32": (_i32, [_vp, _vp, _u64, C.c_int, _vp]),

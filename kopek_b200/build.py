@@ -79,7 +79,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False, 
         obj = os.path.join(OBJ, f"k1_{n}.o")
         jobs.append((obj, [cc, *ARCH, *COMMON, *extra, f"-DKOPEK_K1_N={n}", "-c", os.path.join(CSRC, "k1_inst.cu"),
                            "-o", obj]))
-    for name in ("kopek_cuda", "k1w_inst", "k1m_inst", "fft_large", "synth", "pcm"):
+    for name in ("kopek_cuda", "k1w_inst", "k1m_inst", "fft_large", "synth", "pcm", "dist_fft"):
         src = os.path.join(CSRC, name + ".cu")
         if os.path.exists(src):
             obj = os.path.join(OBJ, name + ".o")

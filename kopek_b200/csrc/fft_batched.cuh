@@ -47,6 +47,12 @@ __host__ __device__ __forceinline__ void dft4(float2 &v0, float2 &v1, float2 &v2
 }
 
 template <int R> struct Dft;
+template <> struct Dft<2> {
+    __host__ __device__ __forceinline__ static void run(float2 *v) {
+        float2 a = v[0] + v[1], b = v[0] - v[1];
+        v[0] = a; v[1] = b;
+    }
+};
 template <> struct Dft<4> {
     __host__ __device__ __forceinline__ static void run(float2 *v) { dft4(v[0], v[1], v[2], v[3]); }
 };

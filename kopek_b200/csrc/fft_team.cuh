@@ -30,12 +30,6 @@
 
 namespace kopek {
 
-template <> struct Dft<2> {
-    __host__ __device__ __forceinline__ static void run(float2 *v) {
-        float2 a = v[0] + v[1], b = v[0] - v[1];
-        v[0] = a; v[1] = b;
-    }
-};
 
 template <int R> struct K1MGeom {
     static constexpr int T = 16 * R, QD = 16 / R, M = 16 * T, N = 32 * T, S = T + R, S2 = T + 1;

@@ -115,3 +115,88 @@ class PeerSpectrogram:
             else:
                 self._lib.kopek_ipc_close(self._ptr, self.device)
             self._ptr = self._C.c_void_p()
+
+
+# ---- one large transform over the ranks -----------------------------------------------------
+def dist_fft_layout(n: int, world: int, rank: int):
+    """Index bookkeeping of DistributedFFT: (input indices of this rank, output indices of this rank as [world, block]).
+
+    Input: the cyclic slice x[j * world + rank], j < n / world.  Output: out[q][i] = X[(rank * block + i) + L * q] with
+    L = n / world, block = L / world."""
+    import numpy as np
+    L = n // world
+    block = L // world
+    src = np.arange(L, dtype=np.int64) * world + rank
+    dst = (rank * block + np.arange(block, dtype=np.int64))[None, :] + L * np.arange(world, dtype=np.int64)[:, None]
+    return src, dst
+
+
+class DistributedFFT:
+    """One complex-f32 transform of n = world * L points over `world` GPUs (one process per GPU, world in {2, 4, 8}).
+
+    Rank r holds the cyclic slice x[j * world + r].  `forward` runs the four-step transform on the local slice
+    (kopek_fft_large_c2c_f32: no traffic), then ONE kernel per rank finishes its block of bins, reading the other ranks'
+    partial spectra straight out of their HBM over NVLink (CUDA-IPC peer mappings; kopek_fft_dist_combine) while it
+    applies the inter-rank twiddle and the radix-`world` butterfly -- the exchange and the arithmetic are one kernel.
+    Output layout: see dist_fft_layout.  L must be a power of two in [2^16, 2^24]."""
+
+    def __init__(self, n: int, local_device: int, group=None):
+        import ctypes as C
+
+        import torch.distributed as dist
+
+        from . import _lib
+        self._lib, self._check, self._C = _lib.load(), _lib.check, C
+        self.group, self.device = group, local_device
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world not in (2, 4, 8):
+            raise ValueError("DistributedFFT needs 2, 4 or 8 ranks")
+        if n % (self.world * self.world):
+            raise ValueError("n must be a multiple of world^2")
+        self.n, self.L = n, n // self.world
+        self.block = self.L // self.world
+        # this rank's partial spectrum F_r lives in an IPC-exportable allocation; everybody maps everybody's
+        self._own = C.c_void_p()
+        self._check(self._lib.kopek_device_alloc(C.byref(self._own), self.L * 8, local_device))
+        raw = (C.c_ubyte * 64)()
+        self._check(self._lib.kopek_ipc_export(self._own, raw))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(raw), group=group)
+        self._peers = []
+        for r in range(self.world):
+            if r == self.rank:
+                self._peers.append(C.c_void_p(self._own.value))
+            else:
+                ptr = C.c_void_p()
+                buf = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+                self._check(self._lib.kopek_ipc_open(buf, local_device, C.byref(ptr)))
+                self._peers.append(ptr)
+        self._table = (C.c_void_p * self.world)(*[p.value for p in self._peers])
+
+    def forward(self, d_in: int, d_out: int, stream: int = 0) -> None:
+        """d_in: L complex64 (the cyclic slice), d_out: [world, block] complex64; both device pointers of this rank."""
+        import torch
+        import torch.distributed as dist
+        self._check(self._lib.kopek_fft_large_c2c_f32(d_in, self._own, self.L, self.device, stream or None))
+        torch.cuda.synchronize(self.device)          # F_r is complete in this rank's HBM ...
+        dist.barrier(group=self.group)               # ... and in everybody else's
+        self._check(self._lib.kopek_fft_dist_combine(self._table, self.world, self.rank, self.L, d_out, self.device,
+                                                     stream or None))
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)               # nobody overwrites its F_r while a peer still reads it
+
+    def combine_only(self, d_out: int, stream: int = 0) -> None:
+        """The exchange kernel alone (timing): F_r must be in place on every rank."""
+        self._check(self._lib.kopek_fft_dist_combine(self._table, self.world, self.rank, self.L, d_out, self.device,
+                                                     stream or None))
+
+    def close(self) -> None:
+        import torch.distributed as dist
+        dist.barrier(group=self.group)
+        for r, p in enumerate(self._peers):
+            if r != self.rank and p:
+                self._lib.kopek_ipc_close(p, self.device)
+        self._peers = []
+        if self._own:
+            self._lib.kopek_device_free(self._own, self.device)
+            self._own = self._C.c_void_p()

@@ -90,6 +90,8 @@ extern "C" {
     pub fn kopek_ipc_export(d_ptr: *const c_void, handle_out: *mut u8) -> kopek_status;
     pub fn kopek_ipc_open(handle: *const u8, device: c_int, d_ptr: *mut *mut c_void) -> kopek_status;
     pub fn kopek_ipc_close(d_ptr: *mut c_void, device: c_int) -> kopek_status;
+    pub fn kopek_fft_dist_combine(d_spectra: *const *const f32, ranks: u32, rank: u32, local_n: u64, d_out: *mut f32,
+                                  device: c_int, cuda_stream: *mut c_void) -> kopek_status;
     pub fn kopek_host_alloc(ptr: *mut *mut c_void, bytes: usize) -> kopek_status;
     pub fn kopek_host_free(ptr: *mut c_void) -> kopek_status;
 

@@ -85,3 +85,59 @@ def test_sharded_stft_gather_nccl(built_lib, tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "SHARDED_OK" in r.stdout and "PEER_DIRECT_OK" in r.stdout and "PEER_BULK_OK" in r.stdout
+
+
+_DIST_FFT_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch, torch.distributed as dist
+from kopek_b200.sharded import DistributedFFT, dist_fft_layout
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+if world not in (2, 4, 8):
+    world_ok = False
+for lg in (18, 22):
+    n = world << lg                                            # local transforms of 2^18 and 2^22 points
+    g = torch.Generator().manual_seed(lg)                      # the same signal on every rank
+    x = torch.view_as_complex(torch.randn(n, 2, generator=g))
+    x[5 * world + 1] += 300.0                                  # something that is not noise
+    src, dst = dist_fft_layout(n, world, rank)
+    mine = x[torch.from_numpy(src)].cuda().contiguous()
+    out = torch.full((world, n // world // world), float("nan"), dtype=torch.complex64, device="cuda")
+    f = DistributedFFT(n, local)
+    f.forward(mine.data_ptr(), out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    ref = torch.fft.fft(x.to(torch.complex128))                 # f64 on the host: the whole transform
+    want = ref[torch.from_numpy(dst.reshape(-1))].reshape(dst.shape)
+    err = ((out.cpu().to(torch.complex128) - want).abs().max() / ref.abs().max()).item()
+    assert err <= 1e-5 * np.log2(n), (lg, err)
+    # second call on new data reuses the mapped buffers
+    y = torch.view_as_complex(torch.randn(n, 2, generator=g))
+    mine2 = y[torch.from_numpy(src)].cuda().contiguous()
+    f.forward(mine2.data_ptr(), out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    want2 = torch.fft.fft(y.to(torch.complex128))[torch.from_numpy(dst.reshape(-1))].reshape(dst.shape)
+    err2 = ((out.cpu().to(torch.complex128) - want2).abs().max() / want2.abs().max()).item()
+    assert err2 <= 1e-5 * np.log2(n), (lg, err2)
+    f.close()
+    if rank == 0:
+        print("DIST_FFT_OK", world, n, f"{err:.2e}")
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_one_large_transform_over_all_gpus(built_lib, tmp_path):
+    """SURVEY.md 8f row 4: a single transform of world * 2^22 points, the inter-rank butterfly done by ONE kernel per
+    rank that reads the peers' partial spectra over NVLink; checked against an f64 transform of the whole signal."""
+    import torch
+    world = torch.cuda.device_count()
+    world = 8 if world >= 8 else 4 if world >= 4 else 2 if world >= 2 else 0
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    script = tmp_path / "dist_fft_worker.py"
+    script.write_text(_DIST_FFT_WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29900 + os.getpid() % 90), str(script), ROOT]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("DIST_FFT_OK") == 2
