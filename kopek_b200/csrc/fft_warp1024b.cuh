@@ -144,7 +144,7 @@ k1w_1024b_kernel(const K1WParams p) {
             // par = 0: i = 0 -> bands 0..2 by k1, i = 1 -> band 3, i = 2, 3 -> band 4, i >= 4 -> band 5; M - k is band 7.
             constexpr float ysc = WIN ? 1.0f : 0.5f;
             float part[4] = {0.f, 0.f, 0.f, 0.f};            // i = 0 | i = 1 | i = 2, 3 | i >= 4
-            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            float hi = 0.0f;                                 // bins M - k: log band 7
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 if (OUT == OUT_BANDS_LOW && (i == 0 || i > 2)) continue;       // bins 20..43 only: i = 1, 2 of the par = 0 lanes
@@ -153,28 +153,54 @@ k1w_1024b_kernel(const K1WParams p) {
                 float2 D = make_float2(A.x - B.x, A.y + B.y);
                 float2 Q = cmul(mul_w64(D, i), pw_lane);
                 const float2 X1 = S + Q;
-                const float y1 = ysc * fast_sqrt(X1.x * X1.x + X1.y * X1.y);
+                part[i == 0 ? 0 : i == 1 ? 1 : i < 4 ? 2 : 3] += ysc * fast_sqrt(X1.x * X1.x + X1.y * X1.y);
                 if constexpr (OUT == OUT_BANDS_LOG) {
-                    part[i == 0 ? 0 : i == 1 ? 1 : i < 4 ? 2 : 3] += y1;
                     const float2 X2 = make_float2(S.x - Q.x, Q.y - S.y);
                     const float y2 = ysc * fast_sqrt(X2.x * X2.x + X2.y * X2.y);
-                    acc[7] += (i == 0 && l == 0) ? 0.0f : y2;                  // k = 0 pairs with bin 512: not in a band
-                } else {
-                    band_add<0, 7>(acc, par ? -1 : band_low_of(k1 + 16 * i), y1);
+                    hi += (i == 0 && l == 0) ? 0.0f : y2;                      // k = 0 pairs with bin 512: not in a band
                 }
             }
+            // Warp reductions.  Every band's contributors are known lanes, so instead of eight full butterflies
+            // (40 shuffles) the sums ride on lane parity and on runs of adjacent lane pairs; lane 0 collects.
+            constexpr unsigned FULL = 0xffffffffu;
+            float acc[8];
             if constexpr (OUT == OUT_BANDS_LOG) {
-                acc[6] = par ? part[0] + part[1] + part[2] + part[3] : 0.0f;
-                acc[5] = par ? 0.0f : part[3];
-                acc[4] = par ? 0.0f : part[2];
-                acc[3] = par ? 0.0f : part[1];
-                band_add<0, 2>(acc, par ? -1 : band_log_of(k1), part[0]);
-                if (l == 0) acc[7] += 2.0f * ysc * fast_sqrt(zu[0].x * zu[0].x + zu[0].y * zu[0].y);   // bin 256
-            }
+                if (l == 0) hi += 2.0f * ysc * fast_sqrt(zu[0].x * zu[0].x + zu[0].y * zu[0].y);   // bin 256
 #pragma unroll
-            for (int bnd = 0; bnd < 8; ++bnd) {
+                for (int sft = 16; sft > 0; sft >>= 1) hi += __shfl_xor_sync(FULL, hi, sft);
+                // odd lanes (bins 128..255): everything is band 6; even lanes: i >= 4 is band 5 -- one value per parity
+                float v65 = par ? part[0] + part[1] + part[2] + part[3] : part[3];
+                // even lanes: i = 2, 3 is band 4, i = 1 band 3: the band-3 term moves to the odd neighbour first
+                const float p1 = __shfl_xor_sync(FULL, part[1], 1);
+                float v43 = par ? p1 : part[2];
 #pragma unroll
-                for (int sft = 16; sft > 0; sft >>= 1) acc[bnd] += __shfl_xor_sync(0xffffffffu, acc[bnd], sft);
+                for (int sft = 16; sft > 1; sft >>= 1) {
+                    v65 += __shfl_xor_sync(FULL, v65, sft);
+                    v43 += __shfl_xor_sync(FULL, v43, sft);
+                }
+                // i = 0 of the even lanes: bins k1 = l / 2 -> bands 0 (lanes 0..7), 1 (8..15), 2 (16..31)
+                float v0 = par ? 0.0f : part[0];
+                v0 += __shfl_xor_sync(FULL, v0, 2);
+                v0 += __shfl_xor_sync(FULL, v0, 4);
+                acc[0] = v0;                                                   // lane 0's own group
+                acc[1] = __shfl_sync(FULL, v0, 8);
+                acc[2] = __shfl_sync(FULL, v0, 16) + __shfl_sync(FULL, v0, 24);
+                acc[3] = __shfl_sync(FULL, v43, 1);
+                acc[4] = v43;
+                acc[5] = v65;
+                acc[6] = __shfl_sync(FULL, v65, 1);
+                acc[7] = hi;
+            } else {
+                // bins 20..43 sit in the even lanes: i = 1 -> bin 16 + k1 (k1 >= 4), i = 2 -> bin 32 + k1 (k1 < 12); a band
+                // is three consecutive k1 = three consecutive even lanes, summed by two shuffles from the lanes above
+                float u = part[1], v = part[2];
+                u += __shfl_down_sync(FULL, u, 2) + __shfl_down_sync(FULL, u, 4);
+                v += __shfl_down_sync(FULL, v, 2) + __shfl_down_sync(FULL, v, 4);
+#pragma unroll
+                for (int bnd = 0; bnd < 4; ++bnd) {
+                    acc[bnd] = __shfl_sync(FULL, u, 8 + 6 * bnd);              // k1 = 4 + 3 b: bins 20 + 3 b ..
+                    acc[4 + bnd] = __shfl_sync(FULL, v, 6 * bnd);              // k1 = 3 b:     bins 32 + 3 b ..
+                }
             }
             if (l == 0) {
                 constexpr float inv_log[8] = {1.f / 4, 1.f / 4, 1.f / 8, 1.f / 16, 1.f / 32, 1.f / 64, 1.f / 128, 1.f / 256};
