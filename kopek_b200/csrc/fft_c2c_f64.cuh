@@ -39,10 +39,14 @@ __global__ void k2_c2c_f64_chunk(const double2 *__restrict__ in, size_t n_in, si
     in += (size_t)blockIdx.y * in_stride;
     out += (size_t)blockIdx.y * out_stride;
 
-    for (uint32_t p = threadIdx.x; p < cn; p += blockDim.x) {
-        // position base+p of the bit-reversed order holds input element bitrev(base+p)
-        size_t src = k2_bitrev((uint32_t)(base + p), logn);
-        k2_smem[p] = src < n_in ? in[src] : make_double2(0.0, 0.0);   // zero pad, src/fft.rs:36
+    // Position base+p of the bit-reversed order holds input element bitrev(base+p) = (bitrev_chunk(p) << hi) + bitrev_hi(chunk).
+    // The loop runs over the SOURCE index so that a whole transform in one chunk (n <= 4096: every UI-rate call) reads its
+    // input in order -- full lines even when `in` is mapped host memory read over PCIe -- and scatters in shared memory.
+    const int hi = logn - chunk_log;
+    const size_t src0 = k2_bitrev(blockIdx.x, hi);
+    for (uint32_t q = threadIdx.x; q < cn; q += blockDim.x) {
+        size_t src = ((size_t)q << hi) + src0;
+        k2_smem[k2_bitrev(q, chunk_log)] = src < n_in ? in[src] : make_double2(0.0, 0.0);   // zero pad, src/fft.rs:36
     }
     __syncthreads();
     for (int lv = 1; lv <= chunk_log; ++lv) {

@@ -54,7 +54,7 @@ struct K2Context {
     int device = 0;
     bool init = false;
     cudaStream_t stream = nullptr;
-    void *pinned = nullptr;
+    void *pinned = nullptr, *pinned_dev = nullptr;   // mapped: the device reads/writes it directly on the latency path
     size_t pinned_bytes = 0;
     double2 *d_in = nullptr, *d_out = nullptr;
     size_t d_in_elems = 0, d_out_elems = 0;
@@ -65,6 +65,7 @@ static std::vector<TwiddleTable> g_tw_tables;   // small LRU, most recent last
 
 constexpr int K2_CHUNK_LOG_MAX = 12;       // 4096 complex f64 = 64 KiB of shared memory
 constexpr size_t K2_PINNED_MAX = 8u << 20; // staging through pinned memory up to 8 MiB
+constexpr size_t K2_ZERO_COPY_MAX = 512u << 10;   // in + out of a call served without DMA (mapped pinned memory)
 
 // tw[j] = exp(-i pi (2j)/n) exactly as src/fft.rs:24 builds it:
 //   im = ((-PI) * (i as f64)) / (n as f64), i = 2j;  w = (cos im, sin im)
@@ -171,8 +172,9 @@ static kopek_status k2_ensure(K2Context &c, size_t in_elems, size_t out_elems, s
     if (pinned_bytes > c.pinned_bytes) {
         if (c.pinned) cudaFreeHost(c.pinned);
         c.pinned = nullptr; c.pinned_bytes = 0;
-        KOPEK_CUDA(cudaMallocHost(&c.pinned, pinned_bytes));
+        KOPEK_CUDA(cudaHostAlloc(&c.pinned, pinned_bytes, cudaHostAllocMapped));
         c.pinned_bytes = pinned_bytes;
+        KOPEK_CUDA(cudaHostGetDevicePointer(&c.pinned_dev, c.pinned, 0));
     }
     return KOPEK_OK;
 }
@@ -187,9 +189,27 @@ static kopek_status k2_run_host(const double *in, size_t n_in, size_t batch, dou
     const size_t in_elems = std::max<size_t>(1, n_in * batch), out_elems = n * batch;
     const size_t in_bytes = n_in * batch * sizeof(double2), out_bytes = out_elems * sizeof(double2);
     const bool stage = std::max(in_bytes, out_bytes) <= K2_PINNED_MAX;
-    kopek_status st = k2_ensure(c, in_elems, out_elems, stage ? std::max(in_bytes, out_bytes) : 0);
+    // Latency path (one UI-frame call = 16 KB in, 16 KB out): no DMA at all.  The pinned staging buffer is mapped into
+    // the device's address space, the single-CTA kernel gathers its bit-reversed input straight from it over PCIe and
+    // writes the spectrum back into it, so a call is one launch + one stream synchronisation instead of two copy
+    // launches around the kernel (46 -> ~25 us per 1024-point call).  Same kernel, same bits.
+    const bool zero_copy = stage && n <= ((size_t)1 << K2_CHUNK_LOG_MAX) && in_bytes + out_bytes <= K2_ZERO_COPY_MAX;
+    const size_t out_off = (in_bytes + 255) & ~(size_t)255;
+    kopek_status st = k2_ensure(c, zero_copy ? 1 : in_elems, zero_copy ? 1 : out_elems,
+                                zero_copy ? out_off + out_bytes : stage ? std::max(in_bytes, out_bytes) : 0);
     if (st != KOPEK_OK) return st;
     DeviceGuard g(c.device);
+    if (zero_copy) {
+        double2 *pin_in = reinterpret_cast<double2 *>(c.pinned);
+        double2 *pin_out = reinterpret_cast<double2 *>(reinterpret_cast<char *>(c.pinned) + out_off);
+        if (in_bytes) memcpy(pin_in, in, in_bytes);
+        st = k2_run_device(reinterpret_cast<const double2 *>(c.pinned_dev), n_in, batch,
+                           reinterpret_cast<double2 *>(reinterpret_cast<char *>(c.pinned_dev) + out_off), c.device, c.stream);
+        if (st != KOPEK_OK) return st;
+        KOPEK_CUDA(cudaStreamSynchronize(c.stream));
+        memcpy(out, pin_out, out_bytes);
+        return KOPEK_OK;
+    }
     if (in_bytes) {
         if (stage) {
             memcpy(c.pinned, in, in_bytes);
