@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <new>
 #include <string>
@@ -55,6 +56,8 @@ struct K2Context {
     bool init = false;
     cudaStream_t stream = nullptr;
     void *pinned = nullptr, *pinned_dev = nullptr;   // mapped: the device reads/writes it directly on the latency path
+    uint32_t *flag = nullptr, *flag_dev = nullptr;   // mapped completion word of the latency path
+    uint32_t token = 0;
     size_t pinned_bytes = 0;
     double2 *d_in = nullptr, *d_out = nullptr;
     size_t d_in_elems = 0, d_out_elems = 0;
@@ -98,6 +101,7 @@ static kopek_status k2_get_twiddles(size_t n, int device, const double2 **out) {
     }
     if (g_tw_tables.size() >= 8) {   // evict least recently used
         // the evicted table may still be read by a kernel in flight on some stream
+        DeviceGuard ge(g_tw_tables.front().device);
         cudaDeviceSynchronize();
         cudaFree(g_tw_tables.front().d);
         g_tw_tables.erase(g_tw_tables.begin());
@@ -107,9 +111,11 @@ static kopek_status k2_get_twiddles(size_t n, int device, const double2 **out) {
     return KOPEK_OK;
 }
 
-// Device-resident batched c2c f64.  n = next_pow2(n_in) per transform.
+// Device-resident batched c2c f64.  n = next_pow2(n_in) per transform.  `flag`/`token`: see k2_c2c_f64_chunk; only
+// honoured (and *flag_used set) when the whole call is one single-CTA launch.
 static kopek_status k2_run_device(const double2 *d_in, size_t n_in, size_t batch, double2 *d_out, int device,
-                                  cudaStream_t stream) {
+                                  cudaStream_t stream, volatile uint32_t *flag = nullptr, uint32_t token = 0,
+                                  bool *flag_used = nullptr) {
     const size_t n = kopek_next_pow2(n_in);
     if (n > ((size_t)1 << 30)) return fail(KOPEK_ERR_UNSUPPORTED, "fft length %zu exceeds 2^30", n);
     const int logn = ilog2(n);
@@ -118,28 +124,59 @@ static kopek_status k2_run_device(const double2 *d_in, size_t n_in, size_t batch
     if (st != KOPEK_OK) return st;
     const int chunk_log = std::min(logn, K2_CHUNK_LOG_MAX);
     const size_t smem = sizeof(double2) << chunk_log;
-    static bool attr_done = false;
-    if (!attr_done) {
+    // function attributes belong to the device's context: one flag per device (idempotent, so a race is benign)
+    static std::atomic<bool> attr_done[64];
+    if (device < 0 || device >= 64 || !attr_done[device].load(std::memory_order_acquire)) {
         KOPEK_CUDA(cudaFuncSetAttribute(k2_c2c_f64_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)(sizeof(double2) << K2_CHUNK_LOG_MAX)));
-        attr_done = true;
+        if (device >= 0 && device < 64) attr_done[device].store(true, std::memory_order_release);
     }
     const size_t chunks = n >> chunk_log;
-    const int threads = (int)std::min<size_t>(1024, std::max<size_t>(32, ((size_t)1 << chunk_log) / 2));
+    const int threads = (int)std::max<size_t>(32, ((size_t)1 << chunk_log) / 8);   // one 8-element item per thread
+    const bool use_flag = flag && chunks == 1 && batch == 1;
+    if (flag_used) *flag_used = use_flag;
     for (size_t b0 = 0; b0 < batch; b0 += 65535) {
         size_t nb = std::min<size_t>(65535, batch - b0);
         dim3 grid((unsigned)chunks, (unsigned)nb);
         k2_c2c_f64_chunk<<<grid, threads, smem, stream>>>(d_in + b0 * n_in, n_in, n_in, d_out + b0 * n, n, tw, logn,
-                                                         chunk_log);
+                                                         chunk_log, use_flag ? flag : nullptr, token);
         KOPEK_CUDA(cudaGetLastError());
-        for (int lv = chunk_log + 1; lv <= logn; ++lv)
+        // the levels above the chunk size: global passes of up to three levels each
+        for (int lv = chunk_log + 1; lv <= logn;) {
+            const int r = (logn - lv + 1) % 3 ? (logn - lv + 1) % 3 : 3;
+            const size_t items = n >> r;
             for (size_t b = 0; b < nb; ++b) {
-                size_t nbf = n / 2;
-                k2_c2c_f64_level<<<(unsigned)((nbf + 255) / 256), 256, 0, stream>>>(d_out + (b0 + b) * n, tw, logn, lv);
+                double2 *d = d_out + (b0 + b) * n;
+                const unsigned g = (unsigned)((items + 255) / 256);
+                if (r == 1) k2_c2c_f64_levels<1><<<g, 256, 0, stream>>>(d, tw, logn, lv);
+                else if (r == 2) k2_c2c_f64_levels<2><<<g, 256, 0, stream>>>(d, tw, logn, lv);
+                else k2_c2c_f64_levels<3><<<g, 256, 0, stream>>>(d, tw, logn, lv);
                 KOPEK_CUDA(cudaGetLastError());
             }
+            lv += r;
+        }
     }
     return KOPEK_OK;
+}
+
+// Wait for `token` to land in the mapped flag word: the kernel's last action.  Polling host memory costs a cache miss
+// per look; a stream synchronisation costs several microseconds after the kernel has ended.  The stream is queried
+// now and then so that a failed launch cannot spin forever.
+static kopek_status k2_wait_flag(const volatile uint32_t *flag, uint32_t token, cudaStream_t stream) {
+    for (uint32_t spins = 1;; ++spins) {
+        if (*flag == token) {
+            std::atomic_thread_fence(std::memory_order_acquire);
+            return KOPEK_OK;
+        }
+        if ((spins & 0xFFFu) == 0) {
+            cudaError_t q = cudaStreamQuery(stream);
+            if (q == cudaSuccess) {           // the kernel has ended: its token is on its way or there already
+                KOPEK_CUDA(cudaStreamSynchronize(stream));
+                return KOPEK_OK;
+            }
+            if (q != cudaErrorNotReady) return fail(KOPEK_ERR_CUDA, "fft kernel failed: %s", cudaGetErrorString(q));
+        }
+    }
 }
 
 static kopek_status k2_ensure(K2Context &c, size_t in_elems, size_t out_elems, size_t pinned_bytes) {
@@ -155,6 +192,9 @@ static kopek_status k2_ensure(K2Context &c, size_t in_elems, size_t out_elems, s
     if (!g.ok) return fail(KOPEK_ERR_CUDA, "cannot select device %d", c.device);
     if (!c.init) {
         KOPEK_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        KOPEK_CUDA(cudaHostAlloc(&c.flag, 64, cudaHostAllocMapped));
+        KOPEK_CUDA(cudaHostGetDevicePointer(&c.flag_dev, c.flag, 0));
+        *c.flag = 0;
         c.init = true;
     }
     if (in_elems > c.d_in_elems) {
@@ -203,10 +243,15 @@ static kopek_status k2_run_host(const double *in, size_t n_in, size_t batch, dou
         double2 *pin_in = reinterpret_cast<double2 *>(c.pinned);
         double2 *pin_out = reinterpret_cast<double2 *>(reinterpret_cast<char *>(c.pinned) + out_off);
         if (in_bytes) memcpy(pin_in, in, in_bytes);
+        bool flagged = false;
+        if (++c.token == 0) c.token = 1;
         st = k2_run_device(reinterpret_cast<const double2 *>(c.pinned_dev), n_in, batch,
-                           reinterpret_cast<double2 *>(reinterpret_cast<char *>(c.pinned_dev) + out_off), c.device, c.stream);
+                           reinterpret_cast<double2 *>(reinterpret_cast<char *>(c.pinned_dev) + out_off), c.device, c.stream,
+                           c.flag_dev, c.token, &flagged);
         if (st != KOPEK_OK) return st;
-        KOPEK_CUDA(cudaStreamSynchronize(c.stream));
+        if (flagged) st = k2_wait_flag(c.flag, c.token, c.stream);
+        else KOPEK_CUDA(cudaStreamSynchronize(c.stream));
+        if (st != KOPEK_OK) return st;
         memcpy(out, pin_out, out_bytes);
         return KOPEK_OK;
     }
@@ -854,15 +899,19 @@ kopek_status kopek_stft_exec_host(kopek_plan *plan, const float *h_samples, uint
 }
 
 // ------------------------------------------------------------- live stream ----
+// The beep view's sliding VecDeque of the last n samples (examples/beep/view.rs:44,57-60).  A push is a latency
+// path (a few KB per UI frame), so nothing is copied by DMA: the doubled ring and the spectrum live in MAPPED pinned
+// host memory, the plan's kernel reads the latest n samples from the ring over PCIe (in order) and stores the
+// spectrum straight back -- one launch and one stream synchronisation per push.
 struct kopek_stream {
     kopek_plan *plan;
     uint32_t n;
     int device;
     uint64_t written;          // total samples pushed so far
-    float *d_ring;             // 2n floats: sample i lives at i % n and i % n + n
-    float *h_in;               // pinned staging, n floats
-    void *h_out;               // pinned staging, one spectrum
-    void *d_out;
+    float *h_ring;             // mapped pinned, 2n floats: sample i lives at i % n and i % n + n
+    float *d_ring;             // the device's address of h_ring
+    void *h_out;               // mapped pinned, one spectrum
+    void *d_out;               // the device's address of h_out
     cudaStream_t cs;
     std::mutex mu;
 };
@@ -888,19 +937,19 @@ kopek_status kopek_stream_create(kopek_stream **stream, uint32_t n, uint32_t win
     kopek_stream *s = new (std::nothrow) kopek_stream();
     if (!s) { kopek_plan_destroy(plan); return fail(KOPEK_ERR_NOMEM, "out of host memory"); }
     s->plan = plan; s->n = n; s->device = device; s->written = 0;
-    s->d_ring = nullptr; s->h_in = nullptr; s->h_out = nullptr; s->d_out = nullptr; s->cs = nullptr;
+    s->h_ring = nullptr; s->d_ring = nullptr; s->h_out = nullptr; s->d_out = nullptr; s->cs = nullptr;
     DeviceGuard g(device);
     const size_t ob = plan->bins * plan->elem_bytes;
     cudaError_t e;
-    if ((e = cudaMalloc(&s->d_ring, 2 * n * sizeof(float))) != cudaSuccess ||
-        (e = cudaMemset(s->d_ring, 0, 2 * n * sizeof(float))) != cudaSuccess ||
-        (e = cudaMalloc(&s->d_out, ob)) != cudaSuccess ||
-        (e = cudaMallocHost(&s->h_in, n * sizeof(float))) != cudaSuccess ||
-        (e = cudaMallocHost(&s->h_out, ob)) != cudaSuccess ||
+    if ((e = cudaHostAlloc(&s->h_ring, 2 * n * sizeof(float), cudaHostAllocMapped)) != cudaSuccess ||
+        (e = cudaHostGetDevicePointer(&s->d_ring, s->h_ring, 0)) != cudaSuccess ||
+        (e = cudaHostAlloc(&s->h_out, ob, cudaHostAllocMapped)) != cudaSuccess ||
+        (e = cudaHostGetDevicePointer(&s->d_out, s->h_out, 0)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&s->cs, cudaStreamNonBlocking)) != cudaSuccess) {
         kopek_stream_destroy(s);
         return fail(KOPEK_ERR_CUDA, "stream setup failed: %s", cudaGetErrorString(e));
     }
+    memset(s->h_ring, 0, 2 * n * sizeof(float));      // the VecDeque starts as n zeros
     *stream = s;
     return KOPEK_OK;
 }
@@ -919,26 +968,24 @@ kopek_status kopek_stream_push(kopek_stream *s, const float *h_samples, uint32_t
         count = n;
     }
     if (count) {
-        memcpy(s->h_in, h_samples, count * sizeof(float));
         uint32_t pos = (uint32_t)(s->written % n), done = 0;
         while (done < count) {             // at most two segments (wrap), each written to both ring halves
             uint32_t seg = std::min(count - done, n - pos);
-            KOPEK_CUDA(cudaMemcpyAsync(s->d_ring + pos, s->h_in + done, seg * sizeof(float), cudaMemcpyHostToDevice, s->cs));
-            KOPEK_CUDA(cudaMemcpyAsync(s->d_ring + pos + n, s->h_in + done, seg * sizeof(float), cudaMemcpyHostToDevice, s->cs));
+            memcpy(s->h_ring + pos, h_samples + done, seg * sizeof(float));
+            memcpy(s->h_ring + pos + n, h_samples + done, seg * sizeof(float));
             done += seg;
             pos = (pos + seg) % n;
         }
         s->written += count;
     }
-    // the most recent n samples are contiguous from (written % n) in the doubled ring
+    // the most recent n samples are contiguous from (written % n) in the doubled ring; the launch orders the host's
+    // writes before the kernel's reads, the synchronisation orders the kernel's stores before the host's reads
     const float *frame = s->d_ring + (s->written % n);
     uint64_t nf = 0;
     kopek_status st = kopek_stft_exec(s->plan, frame, n, s->d_out, &nf, s->cs);
     if (st != KOPEK_OK) return st;
-    const size_t ob = s->plan->bins * s->plan->elem_bytes;
-    KOPEK_CUDA(cudaMemcpyAsync(s->h_out, s->d_out, ob, cudaMemcpyDeviceToHost, s->cs));
     KOPEK_CUDA(cudaStreamSynchronize(s->cs));
-    memcpy(h_out, s->h_out, ob);
+    memcpy(h_out, s->h_out, s->plan->bins * s->plan->elem_bytes);
     return KOPEK_OK;
 }
 
@@ -946,9 +993,7 @@ kopek_status kopek_stream_destroy(kopek_stream *s) {
     if (!s) return KOPEK_OK;
     DeviceGuard g(s->device);
     if (s->cs) { cudaStreamSynchronize(s->cs); cudaStreamDestroy(s->cs); }
-    if (s->d_ring) cudaFree(s->d_ring);
-    if (s->d_out) cudaFree(s->d_out);
-    if (s->h_in) cudaFreeHost(s->h_in);
+    if (s->h_ring) cudaFreeHost(s->h_ring);
     if (s->h_out) cudaFreeHost(s->h_out);
     if (s->plan) kopek_plan_destroy(s->plan);
     delete s;
