@@ -112,6 +112,26 @@ def _physical_gpu_index(local_rank: int) -> int:
     return local_rank
 
 
+def bind_near_gpu(index: int):
+    """Pin this rank's threads to the CPUs NVML reports as local to its GPU, BEFORE the pinned host buffers of the
+    e2e leg are allocated, so that they come from the GPU's own NUMA node (eight ranks pulling 150 GB/s through one
+    socket's memory controllers is what bounded the 8-GPU e2e figure).  Returns the number of CPUs, None if unknown."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def cpu_port_rate(frames: int, threads: int):
     """Time the oracle port (restatement of src/fft.rs) on `frames` frames of the workload."""
     import oracle  # CPU baseline leg: the one place bench.py executes oracle/
@@ -205,6 +225,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    all_cpus = os.sched_getaffinity(0)
+    near = bind_near_gpu(_physical_gpu_index(local))
     frames = args.frames
     plan = StftPlan(N_FFT, N_FFT, WINDOW_HANN, OUT_MAG, device=local)
     stream = torch.cuda.current_stream().cuda_stream
@@ -305,7 +327,9 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clocks,
         }
+        line["e2e"]["cpus_near_gpu"] = near
         if world == 1 and not args.no_cpu:
+            os.sched_setaffinity(0, all_cpus)            # the CPU port gets every host core
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -68,6 +68,7 @@ static std::vector<TwiddleTable> g_tw_tables;   // small LRU, most recent last
 
 constexpr int K2_CHUNK_LOG_MAX = 12;       // 4096 complex f64 = 64 KiB of shared memory
 constexpr size_t K2_PINNED_MAX = 8u << 20; // staging through pinned memory up to 8 MiB
+constexpr uint64_t K1_HOST_CHUNK_MB = 16;     // samples per in-flight chunk of kopek_stft_exec_host
 constexpr size_t K2_ZERO_COPY_MAX = 512u << 10;   // in + out of a call served without DMA (mapped pinned memory)
 
 // tw[j] = exp(-i pi (2j)/n) exactly as src/fft.rs:24 builds it:
@@ -858,10 +859,13 @@ kopek_status kopek_stft_exec_host(kopek_plan *plan, const float *h_samples, uint
     DeviceGuard g(plan->device);
     if (!g.ok) return fail(KOPEK_ERR_CUDA, "cannot select device %d", plan->device);
 
-    // chunk so that one slot moves ~32 MiB of samples; three slots keep the H2D
-    // engine, the SMs and the D2H engine busy at the same time
+    // chunk so that one slot moves ~KOPEK_HOST_CHUNK_MB MiB of samples; three slots keep the H2D engine, the SMs
+    // and the D2H engine busy at the same time.  The first upload and the last download are not overlapped with
+    // anything, so the chunk is kept small against the call (measured on B200, tools/sweep_host_chunk.py).
     const uint64_t n = plan->n, hop = plan->hop;
-    uint64_t cf = std::max<uint64_t>(1, ((uint64_t)32 << 20) / (hop * sizeof(float)));
+    uint64_t chunk_mb = K1_HOST_CHUNK_MB;
+    if (const char *env = getenv("KOPEK_HOST_CHUNK_MB")) chunk_mb = std::max(1, atoi(env));
+    uint64_t cf = std::max<uint64_t>(1, (chunk_mb << 20) / (hop * sizeof(float)));
     cf = std::min(cf, frames);
     const uint64_t in_elems = (cf - 1) * hop + n;
     const uint64_t out_bytes = cf * plan->pitch * plan->elem_bytes;
