@@ -21,8 +21,26 @@ namespace kopek {
 
 enum : int { OUT_COMPLEX = 0, OUT_MAG = 1, OUT_POWER = 2, OUT_DB = 3, OUT_BANDS_LOG = 4, OUT_BANDS_LOW = 5 };
 
+// Complex add / subtract.  With -DKOPEK_F32X2 the device side issues ONE packed instruction (add/sub.rn.f32x2, SASS
+// FADD2) on the (re, im) register pair: same results bit for bit (two independent IEEE additions), same FP32 pipe
+// time (tools/micro/fadd2.cu: 128 adds/clk/SM either way), half the issue slots.
+#if defined(KOPEK_F32X2) && defined(__CUDA_ARCH__)
+__device__ __forceinline__ float2 operator+(float2 a, float2 b) {
+    float2 r;
+    asm("{\n\t.reg .b64 pa, pb, pr;\n\tmov.b64 pa, {%2, %3};\n\tmov.b64 pb, {%4, %5};\n\tadd.rn.f32x2 pr, pa, pb;\n\t"
+        "mov.b64 {%0, %1}, pr;\n\t}" : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 operator-(float2 a, float2 b) {
+    float2 r;
+    asm("{\n\t.reg .b64 pa, pb, pr;\n\tmov.b64 pa, {%2, %3};\n\tmov.b64 pb, {%4, %5};\n\tsub.rn.f32x2 pr, pa, pb;\n\t"
+        "mov.b64 {%0, %1}, pr;\n\t}" : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+#else
 __host__ __device__ __forceinline__ float2 operator+(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __host__ __device__ __forceinline__ float2 operator-(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+#endif
 __host__ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }

@@ -22,6 +22,11 @@
 #include <vector>
 
 #include "common.cuh"
+// complex add / subtract as ONE packed instruction (add/sub.rn.f32x2 -> SASS FADD2) in this translation unit: the two
+// passes run under a 64-register cap with a quarter of their instructions in address arithmetic, and 11 % fewer
+// issue slots are worth 3.4 % at 2^24 (0.1464 -> 0.1415 ms).  The batched kernels gain nothing from it (measured,
+// profiles/r1_f32x2_sweep.txt), so they keep the scalar form.
+#define KOPEK_F32X2
 #include "fft_batched.cuh"
 #include "fft_warp1024.cuh"
 
