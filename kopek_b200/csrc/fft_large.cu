@@ -17,6 +17,7 @@
 // (column index fastest across lanes), which keeps every shared access contiguous.
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <vector>
@@ -38,6 +39,36 @@ template <> struct K3Cfg<512>  { static constexpr int R0 = 8,  R1 = 8,  R2 = 8; 
 template <> struct K3Cfg<1024> { static constexpr int R0 = 4,  R1 = 16, R2 = 16; };
 template <> struct K3Cfg<2048> { static constexpr int R0 = 8,  R1 = 16, R2 = 16; };
 template <> struct K3Cfg<4096> { static constexpr int R0 = 16, R1 = 16, R2 = 16; };
+
+// ---- radix 64 in registers: n = a + 4 b, k = kb + 16 ka:  X[k] = sum_a W4^{a ka} W64^{a kb} sum_b v[a + 4 b] W16^{b kb}
+// W64^k = exp(-2 pi i k / 64); called with compile-time k after unrolling, so the values become immediates
+__host__ __device__ __forceinline__ float2 k3_w64(int k) {
+    constexpr float re[64] = {1.0f, 0.9951847266721969f, 0.9807852804032304f, 0.9569403357322088f, 0.9238795325112867f, 0.881921264348355f, 0.8314696123025452f, 0.773010453362737f, 0.7071067811865476f, 0.6343932841636455f, 0.5555702330196023f, 0.4713967368259978f, 0.38268343236508984f, 0.29028467725446233f, 0.19509032201612833f, 0.09801714032956077f, 0.0f, -0.09801714032956065f, -0.1950903220161282f, -0.29028467725446216f, -0.3826834323650897f, -0.4713967368259977f, -0.555570233019602f, -0.6343932841636454f, -0.7071067811865475f, -0.773010453362737f, -0.8314696123025453f, -0.8819212643483549f, -0.9238795325112867f, -0.9569403357322088f, -0.9807852804032304f, -0.9951847266721968f, -1.0f, -0.9951847266721969f, -0.9807852804032304f, -0.9569403357322089f, -0.9238795325112868f, -0.881921264348355f, -0.8314696123025455f, -0.7730104533627371f, -0.7071067811865477f, -0.6343932841636459f, -0.5555702330196022f, -0.47139673682599786f, -0.38268343236509034f, -0.29028467725446244f, -0.19509032201612866f, -0.09801714032956045f, 0.0f, 0.09801714032956009f, 0.1950903220161283f, 0.29028467725446205f, 0.38268343236509f, 0.4713967368259976f, 0.5555702330196018f, 0.6343932841636456f, 0.7071067811865474f, 0.7730104533627367f, 0.8314696123025452f, 0.8819212643483548f, 0.9238795325112865f, 0.9569403357322088f, 0.9807852804032303f, 0.9951847266721969f};
+    constexpr float im[64] = {0.0f, -0.0980171403295606f, -0.19509032201612825f, -0.29028467725446233f, -0.3826834323650898f, -0.47139673682599764f, -0.5555702330196022f, -0.6343932841636455f, -0.7071067811865475f, -0.773010453362737f, -0.8314696123025452f, -0.8819212643483549f, -0.9238795325112867f, -0.9569403357322089f, -0.9807852804032304f, -0.9951847266721968f, -1.0f, -0.9951847266721969f, -0.9807852804032304f, -0.9569403357322089f, -0.9238795325112867f, -0.881921264348355f, -0.8314696123025455f, -0.7730104533627371f, -0.7071067811865476f, -0.6343932841636455f, -0.5555702330196022f, -0.47139673682599786f, -0.3826834323650899f, -0.2902846772544624f, -0.1950903220161286f, -0.09801714032956083f, 0.0f, 0.09801714032956059f, 0.19509032201612836f, 0.2902846772544621f, 0.38268343236508967f, 0.47139673682599764f, 0.555570233019602f, 0.6343932841636453f, 0.7071067811865475f, 0.7730104533627367f, 0.8314696123025452f, 0.8819212643483549f, 0.9238795325112865f, 0.9569403357322088f, 0.9807852804032303f, 0.9951847266721969f, 1.0f, 0.9951847266721969f, 0.9807852804032304f, 0.9569403357322089f, 0.9238795325112866f, 0.881921264348355f, 0.8314696123025455f, 0.7730104533627369f, 0.7071067811865477f, 0.6343932841636459f, 0.5555702330196022f, 0.4713967368259979f, 0.3826834323650904f, 0.2902846772544625f, 0.19509032201612872f, 0.0980171403295605f};
+    return make_float2(re[k], im[k]);
+}
+template <> struct Dft<64> {
+    __host__ __device__ __forceinline__ static void run(float2 *v) {
+        float2 u[4][16];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+#pragma unroll
+            for (int b = 0; b < 16; ++b) u[a][b] = v[a + 4 * b];
+            Dft<16>::run(u[a]);
+            if (a > 0) {
+#pragma unroll
+                for (int kb = 1; kb < 16; ++kb)
+                    u[a][kb] = cmul(u[a][kb], k3_w64(a * kb));
+            }
+        }
+#pragma unroll
+        for (int kb = 0; kb < 16; ++kb) {
+            dft4(u[0][kb], u[1][kb], u[2][kb], u[3][kb]);
+#pragma unroll
+            for (int ka = 0; ka < 4; ++ka) v[kb + 16 * ka] = u[ka][kb];
+        }
+    }
+};
 
 __host__ __device__ constexpr int k3_swz(int q) { return q ^ ((q >> 4) & 15); }
 
@@ -271,6 +302,76 @@ k3_pass2(const float2 *__restrict__ mid, float2 *__restrict__ outp, K3Tables tb,
     }
 }
 
+// ---- pass 2, N2 = 4096, as TWO stages of radix 64 (64 x 64) instead of three of radix 16.
+// A thread carries 64 values (128 registers) through a register-resident 64-point transform, so the tile crosses
+// shared memory once between the stages instead of twice, every shared access is base + compile-time offset (the
+// exchange is PADDED -- element q sits at q + (q >> 6) -- where the radix-16 path needs an XOR per access), and the
+// stage table is read 63 times per 64 points.  256 threads per CTA (64 per row, four rows interleaved).
+constexpr int K3R_TILE_F2 = 4096 * 4;                    // dense tile as it lands
+constexpr int K3R_EX_F2 = (4096 + 64) * 4;               // padded exchange, in place over the landing buffer
+constexpr int K3R_TW_F2 = 63 * 64;                       // [t-1][kk] = W4096^{kk t}
+constexpr int K3R_SMEM = K3R_EX_F2 * 8 + K3R_TW_F2 * 8 + 16;
+
+__global__ void __launch_bounds__(256, 1)
+k3_pass2_r64(const float2 *__restrict__ mid, float2 *__restrict__ outp, const float2 *__restrict__ tw_r64, int n_tiles) {
+    extern __shared__ __align__(128) unsigned char k3_smem[];
+    float2 *buf = reinterpret_cast<float2 *>(k3_smem);
+    float2 *s_tw = buf + K3R_EX_F2;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(s_tw + K3R_TW_F2);
+    for (int i = threadIdx.x; i < K3R_TW_F2; i += 256) s_tw[i] = tw_r64[i];
+    constexpr int BYTES = K3R_TILE_F2 * 8, CH = 16384;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if ((int)blockIdx.x < n_tiles) {
+            mbar_expect_tx(bar, BYTES);
+            const char *src = reinterpret_cast<const char *>(mid) + (size_t)blockIdx.x * BYTES;
+            for (int off = 0; off < BYTES; off += CH) tma_load_1d(k3_smem + off, src + off, CH, bar);
+        }
+    }
+    __syncthreads();
+    const int c = threadIdx.x & 3, tid = threadIdx.x >> 2;
+    const size_t n1 = (size_t)n_tiles * 4;
+    const float2 *rdA = buf + (tid >> 1) * 8 + 2 * c + (tid & 1);    // tile-major [n2/2][k1%4][n2%2], n2 = tid + 64 t
+    float2 *wrA = buf + (65 * tid) * 4 + c;                           // q = 64 tid + k  ->  65 tid + k
+    const float2 *rdB = buf + tid * 4 + c;                            // q = tid + 64 t  ->  tid + 65 t
+    const float2 *twB = s_tw + tid;
+    uint32_t phase = 0;
+    for (int u = blockIdx.x; u < n_tiles; u += gridDim.x) {
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        float2 v[64];
+#pragma unroll
+        for (int t = 0; t < 64; ++t) v[t] = rdA[256 * t];
+        __syncthreads();                                              // the exchange overwrites the landing buffer
+        Dft<64>::run(v);
+#pragma unroll
+        for (int k = 0; k < 64; ++k) wrA[4 * k] = v[k];
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < 64; ++t) {
+            float2 x = rdB[260 * t];
+            v[t] = t ? cmul(x, twB[64 * (t - 1)]) : x;
+        }
+        __syncthreads();
+        // the buffer is free: the next tile lands while this one is finished and stored from registers
+        const int nxt = u + gridDim.x;
+        if (threadIdx.x == 0 && nxt < n_tiles) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar, BYTES);
+            const char *src = reinterpret_cast<const char *>(mid) + (size_t)nxt * BYTES;
+            for (int off = 0; off < BYTES; off += CH) tma_load_1d(k3_smem + off, src + off, CH, bar);
+        }
+        Dft<64>::run(v);
+        // X[k1 + N1 k2], k1 = 4 u + c, k2 = tid + 64 k: the 8 lanes x 4 rows of a warp write eight 32-byte runs
+        float2 *dst = outp + 4 * (size_t)u + c + (size_t)tid * n1;
+        const size_t step = 64 * n1;
+#pragma unroll
+        for (int k = 0; k < 64; ++k) { *dst = v[k]; dst += step; }
+    }
+}
+
 // ------------------------------------------------------------------------- host ----
 typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                               const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -308,6 +409,7 @@ struct K3Plan {
     int device = -1;
     int n1 = 0, n2 = 0;
     float2 *tw1 = nullptr, *tw2 = nullptr, *hi = nullptr, *lo = nullptr, *mid = nullptr;
+    float2 *tw2r = nullptr;    // N2 = 4096: stage table of the two-stage radix-64 pass 2
 };
 static std::mutex g_k3_mu;
 static std::vector<K3Plan> g_k3_plans;
@@ -365,16 +467,25 @@ static kopek_status k3_get_plan(uint64_t n, int device, K3Plan *out) {
         return cudaMalloc(d, h.size() * sizeof(float2)) == cudaSuccess &&
                cudaMemcpy(*d, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice) == cudaSuccess;
     };
-    if (!up(&p.tw1, t1) || !up(&p.tw2, t2) || !up(&p.hi, hi) || !up(&p.lo, lo) ||
+    std::vector<float2> t2r;
+    if (p.n2 == 4096) {
+        t2r.resize(K3R_TW_F2);
+        for (int t = 1; t < 64; ++t)
+            for (int kk = 0; kk < 64; ++kk) {
+                double th = -2.0 * M_PI * (double)(kk * t) / 4096.0;
+                t2r[(t - 1) * 64 + kk] = make_float2((float)cos(th), (float)sin(th));
+            }
+    }
+    if (!up(&p.tw1, t1) || !up(&p.tw2, t2) || !up(&p.hi, hi) || !up(&p.lo, lo) || (!t2r.empty() && !up(&p.tw2r, t2r)) ||
         cudaMalloc(&p.mid, n * sizeof(float2)) != cudaSuccess) {
-        cudaFree(p.tw1); cudaFree(p.tw2); cudaFree(p.hi); cudaFree(p.lo); cudaFree(p.mid);
+        cudaFree(p.tw1); cudaFree(p.tw2); cudaFree(p.hi); cudaFree(p.lo); cudaFree(p.mid); cudaFree(p.tw2r);
         return fail(KOPEK_ERR_NOMEM, "four-step plan for n=%llu: %s", (unsigned long long)n,
                     cudaGetErrorString(cudaGetLastError()));
     }
     if (g_k3_plans.size() >= 4) {       // keep the cache (and its n-sized workspaces) small
         cudaDeviceSynchronize();
         K3Plan &o = g_k3_plans.front();
-        cudaFree(o.tw1); cudaFree(o.tw2); cudaFree(o.hi); cudaFree(o.lo); cudaFree(o.mid);
+        cudaFree(o.tw1); cudaFree(o.tw2); cudaFree(o.hi); cudaFree(o.lo); cudaFree(o.mid); cudaFree(o.tw2r);
         g_k3_plans.erase(g_k3_plans.begin());
     }
     g_k3_plans.push_back(p);
@@ -448,7 +559,21 @@ extern "C" kopek_status kopek_fft_large_c2c_f32(const float *d_in, float *d_out,
         case 512: e = launch_pass2<512>(p.n1 / 4, sms, p.mid, reinterpret_cast<float2 *>(d_out), tb, stream); break;
         case 1024: e = launch_pass2<1024>(p.n1 / 4, sms, p.mid, reinterpret_cast<float2 *>(d_out), tb, stream); break;
         case 2048: e = launch_pass2<2048>(p.n1 / 4, sms, p.mid, reinterpret_cast<float2 *>(d_out), tb, stream); break;
-        case 4096: e = launch_pass2<4096>(p.n1 / 4, sms, p.mid, reinterpret_cast<float2 *>(d_out), tb, stream); break;
+        case 4096: {
+            static const bool r64 = !(getenv("KOPEK_K3_R64") && atoi(getenv("KOPEK_K3_R64")) == 0);   // tuning switch
+            if (r64) {
+                const int tiles = p.n1 / 4;
+                e = cudaFuncSetAttribute(k3_pass2_r64, cudaFuncAttributeMaxDynamicSharedMemorySize, K3R_SMEM);
+                if (e == cudaSuccess) {
+                    k3_pass2_r64<<<tiles < sms ? tiles : sms, 256, K3R_SMEM, stream>>>(p.mid, reinterpret_cast<float2 *>(d_out),
+                                                                                     p.tw2r, tiles);
+                    e = cudaGetLastError();
+                }
+            } else {
+                e = launch_pass2<4096>(p.n1 / 4, sms, p.mid, reinterpret_cast<float2 *>(d_out), tb, stream);
+            }
+            break;
+        }
         default: e = cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "four-step pass 2 (N2=%d): %s", p.n2, cudaGetErrorString(e));
