@@ -40,36 +40,6 @@ template <> struct K3Cfg<1024> { static constexpr int R0 = 4,  R1 = 16, R2 = 16;
 template <> struct K3Cfg<2048> { static constexpr int R0 = 8,  R1 = 16, R2 = 16; };
 template <> struct K3Cfg<4096> { static constexpr int R0 = 16, R1 = 16, R2 = 16; };
 
-// ---- radix 64 in registers: n = a + 4 b, k = kb + 16 ka:  X[k] = sum_a W4^{a ka} W64^{a kb} sum_b v[a + 4 b] W16^{b kb}
-// W64^k = exp(-2 pi i k / 64); called with compile-time k after unrolling, so the values become immediates
-__host__ __device__ __forceinline__ float2 k3_w64(int k) {
-    constexpr float re[64] = {1.0f, 0.9951847266721969f, 0.9807852804032304f, 0.9569403357322088f, 0.9238795325112867f, 0.881921264348355f, 0.8314696123025452f, 0.773010453362737f, 0.7071067811865476f, 0.6343932841636455f, 0.5555702330196023f, 0.4713967368259978f, 0.38268343236508984f, 0.29028467725446233f, 0.19509032201612833f, 0.09801714032956077f, 0.0f, -0.09801714032956065f, -0.1950903220161282f, -0.29028467725446216f, -0.3826834323650897f, -0.4713967368259977f, -0.555570233019602f, -0.6343932841636454f, -0.7071067811865475f, -0.773010453362737f, -0.8314696123025453f, -0.8819212643483549f, -0.9238795325112867f, -0.9569403357322088f, -0.9807852804032304f, -0.9951847266721968f, -1.0f, -0.9951847266721969f, -0.9807852804032304f, -0.9569403357322089f, -0.9238795325112868f, -0.881921264348355f, -0.8314696123025455f, -0.7730104533627371f, -0.7071067811865477f, -0.6343932841636459f, -0.5555702330196022f, -0.47139673682599786f, -0.38268343236509034f, -0.29028467725446244f, -0.19509032201612866f, -0.09801714032956045f, 0.0f, 0.09801714032956009f, 0.1950903220161283f, 0.29028467725446205f, 0.38268343236509f, 0.4713967368259976f, 0.5555702330196018f, 0.6343932841636456f, 0.7071067811865474f, 0.7730104533627367f, 0.8314696123025452f, 0.8819212643483548f, 0.9238795325112865f, 0.9569403357322088f, 0.9807852804032303f, 0.9951847266721969f};
-    constexpr float im[64] = {0.0f, -0.0980171403295606f, -0.19509032201612825f, -0.29028467725446233f, -0.3826834323650898f, -0.47139673682599764f, -0.5555702330196022f, -0.6343932841636455f, -0.7071067811865475f, -0.773010453362737f, -0.8314696123025452f, -0.8819212643483549f, -0.9238795325112867f, -0.9569403357322089f, -0.9807852804032304f, -0.9951847266721968f, -1.0f, -0.9951847266721969f, -0.9807852804032304f, -0.9569403357322089f, -0.9238795325112867f, -0.881921264348355f, -0.8314696123025455f, -0.7730104533627371f, -0.7071067811865476f, -0.6343932841636455f, -0.5555702330196022f, -0.47139673682599786f, -0.3826834323650899f, -0.2902846772544624f, -0.1950903220161286f, -0.09801714032956083f, 0.0f, 0.09801714032956059f, 0.19509032201612836f, 0.2902846772544621f, 0.38268343236508967f, 0.47139673682599764f, 0.555570233019602f, 0.6343932841636453f, 0.7071067811865475f, 0.7730104533627367f, 0.8314696123025452f, 0.8819212643483549f, 0.9238795325112865f, 0.9569403357322088f, 0.9807852804032303f, 0.9951847266721969f, 1.0f, 0.9951847266721969f, 0.9807852804032304f, 0.9569403357322089f, 0.9238795325112866f, 0.881921264348355f, 0.8314696123025455f, 0.7730104533627369f, 0.7071067811865477f, 0.6343932841636459f, 0.5555702330196022f, 0.4713967368259979f, 0.3826834323650904f, 0.2902846772544625f, 0.19509032201612872f, 0.0980171403295605f};
-    return make_float2(re[k], im[k]);
-}
-template <> struct Dft<64> {
-    __host__ __device__ __forceinline__ static void run(float2 *v) {
-        float2 u[4][16];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-#pragma unroll
-            for (int b = 0; b < 16; ++b) u[a][b] = v[a + 4 * b];
-            Dft<16>::run(u[a]);
-            if (a > 0) {
-#pragma unroll
-                for (int kb = 1; kb < 16; ++kb)
-                    u[a][kb] = cmul(u[a][kb], k3_w64(a * kb));
-            }
-        }
-#pragma unroll
-        for (int kb = 0; kb < 16; ++kb) {
-            dft4(u[0][kb], u[1][kb], u[2][kb], u[3][kb]);
-#pragma unroll
-            for (int ka = 0; ka < 4; ++ka) v[kb + 16 * ka] = u[ka][kb];
-        }
-    }
-};
-
 __host__ __device__ constexpr int k3_swz(int q) { return q ^ ((q >> 4) & 15); }
 
 // One Stockham stage on 4 interleaved columns: element (q, c) lives at buf[pos(q) * 4 + c].
