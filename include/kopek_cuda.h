@@ -137,7 +137,8 @@ KOPEK_API kopek_status kopek_host_free(void *ptr);
 /* ---- 2b. live sliding window (examples/beep/view.rs:44,57-60,140-158) -----------------------
  * The beep view keeps the most recent 1024 samples in a VecDeque (new samples pushed at the back, old
  * ones popped at the front) and transforms the whole deque once per UI frame.  A kopek_stream is that
- * deque on the device: push() appends `count` new host samples (history starts as zeros), then writes
+ * deque for the device (a ring in mapped pinned host memory which the kernel reads in place: one launch per
+ * push, no DMA): push() appends `count` new host samples (history starts as zeros), then writes
  * the spectrum of the most recent n samples to h_out (kopek_stream_bins() elements, f32 or (re,im) f32).
  * input_scale multiplies every sample before the transform (1/32767 in beep/view.rs:143, 1 in pong). */
 typedef struct kopek_stream kopek_stream;

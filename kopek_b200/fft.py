@@ -198,7 +198,7 @@ class StftPlan:
 
 class LiveSpectrum:
     """Sliding-window analyser of the live examples (kopek_stream_*): the VecDeque of the most recent n samples
-    of examples/beep/view.rs:44,57-60 kept on the device; `push(new_samples)` returns the spectrum of the
+    of examples/beep/view.rs:44,57-60 kept in mapped pinned memory the kernel reads directly; `push(new_samples)` returns the spectrum of the
     window that ends at the newest sample (history starts as zeros)."""
 
     def __init__(self, n: int = 1024, window: int = WINDOW_RECT, output: int = OUT_MAG, input_scale: float = 1.0,
