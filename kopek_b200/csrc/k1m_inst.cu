@@ -74,9 +74,13 @@ void k1m_build_tables(int n, const float *half_window, double cs_a, double cs_b,
 #endif
 // resident teams per SM the register allocation is held to: 12 warps per SM (168 registers) for the rectangular and
 // cosine-sum windows -- measured 76 -> 86 % (N = 2048) and 70 -> 80 % (N = 4096) against 8 warps -- and 8 warps for
-// the table window, whose 32 extra registers would otherwise spill
+// the table window, whose 32 extra registers would otherwise spill.  16 warps (-DKOPEK_K1M_WARPS=16: 128 registers,
+// ~110 bytes of spills) is far worse: 84 -> 64 % (N = 2048) and 76 -> 57 % (N = 4096).
+#ifndef KOPEK_K1M_WARPS
+#define KOPEK_K1M_WARPS 12
+#endif
 template <int R, int WINK> struct K1MOcc {
-    static constexpr int MINB = R == 8 ? (WINK == 1 ? 2 : 3) : R == 4 ? (WINK == 1 ? 4 : 6) : 12;
+    static constexpr int MINB = WINK == 1 ? 8 * 2 / R : KOPEK_K1M_WARPS * 2 / R;
 };
 
 template <int R, int OUT, int WIN>
