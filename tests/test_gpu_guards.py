@@ -44,7 +44,7 @@ def test_stft_kernels_stay_in_bounds(built_lib, n, hop, window, output):
     assert bool((xin[:GUARD] == SENT).all()) and bool((xin[GUARD + ns:] == SENT).all())
 
 
-@pytest.mark.parametrize("log_n", [16, 19, 22])
+@pytest.mark.parametrize("log_n", [16, 19, 22, 23, 24])      # 23, 24: the radix-64 pass 2
 def test_large_fft_stays_in_bounds(built_lib, log_n):
     import torch
     from kopek_b200 import fft
