@@ -132,6 +132,16 @@ def bind_near_gpu(index: int):
     return None
 
 
+def claim_stdout():
+    """stdout carries ONE JSON line.  Libraries print there too (NCCL writes its version banner to stdout when
+    NCCL_DEBUG is set), so file descriptor 1 is pointed at stderr for the rest of the process and the line is written
+    to the descriptor stdout had when the process started."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def cpu_port_rate(frames: int, threads: int):
     """Time the oracle port (restatement of src/fft.rs) on `frames` frames of the workload."""
     import oracle  # CPU baseline leg: the one place bench.py executes oracle/
@@ -161,6 +171,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    out = claim_stdout()
     import oracle
     oracle.build()
     cores = oracle.max_threads()
@@ -186,7 +197,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
     return 0
 
 
@@ -213,6 +224,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    out_stream = claim_stdout()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: kopek_b200 has no CPU fallback")
     torch.cuda.set_device(local)
@@ -331,7 +343,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             os.sched_setaffinity(0, all_cpus)            # the CPU port gets every host core
             line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out_stream, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -11,6 +11,7 @@ def test_reference_arm_json_line(oracle_mod):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
+    assert len(r.stdout.strip().splitlines()) == 1, "stdout must carry exactly one line"
     line = json.loads(r.stdout.strip().splitlines()[-1])
     for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
@@ -35,3 +36,14 @@ def test_gpu_arm_needs_a_gpu():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True,
                        timeout=300)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_library_chatter_on_stdout_does_not_reach_the_json_line():
+    """NCCL prints its version banner to file descriptor 1 when NCCL_DEBUG is set: bench.py points that descriptor at
+    stderr and writes its one line to the stdout it was started with."""
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; out = bench.claim_stdout(); "
+            "os.write(1, b'NCCL version x.y\\n'); print('chatter'); print('{\"ok\": 1}', file=out, flush=True)" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == '{"ok": 1}\n'
+    assert "NCCL version" in r.stderr and "chatter" in r.stderr
