@@ -68,7 +68,9 @@ class PeerSpectrogram:
     `dst` allocates the buffer (kopek_device_alloc) and broadcasts its CUDA IPC handle; the other ranks map it
     (kopek_ipc_open) and pass `row_ptr(f0)` as d_out of StftPlan.exec_ptr, so K1/K1W store their bins straight
     into the owner's HBM over NVLink -- transform and transfer are one kernel, no gather afterwards.
-    Call `finish()` (device sync + barrier) before the owner reads; `to_host()` / `copy_to(ptr)` on the owner.
+    Call `finish()` (device sync + barrier) before the owner reads; `copy_to(ptr)` on the owner.  `close()` is not
+    collective: the importing ranks close first, then (after a barrier of the caller's) the owner -- CUDA IPC requires
+    every mapping to be gone before the exporting process frees the allocation.
     """
 
     def __init__(self, n_frames_total: int, pitch: int, elem_bytes: int, local_device: int, dst: int = 0, group=None):
@@ -197,6 +199,7 @@ class DistributedFFT:
             if r != self.rank and p:
                 self._lib.kopek_ipc_close(p, self.device)
         self._peers = []
+        dist.barrier(group=self.group)               # every importer has unmapped before an owner frees (CUDA IPC rule)
         if self._own:
             self._lib.kopek_device_free(self._own, self.device)
             self._own = self._C.c_void_p()
