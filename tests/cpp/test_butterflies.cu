@@ -1,4 +1,4 @@
-// Host-side check of the radix-4/8/16 register butterflies of K1 against a
+// Host-side check of the radix-2/4/8/16/64 register butterflies (K1 family, K3 pass 2) against a
 // direct f64 DFT.  Built and run by tests/test_host_logic.py (no GPU needed).
 #include <cmath>
 #include <cstdio>
@@ -32,7 +32,7 @@ template <int R> static double check() {
 }
 
 int main() {
-    double e4 = check<4>(), e8 = check<8>(), e16 = check<16>();
-    printf("dft4 %.3e dft8 %.3e dft16 %.3e\n", e4, e8, e16);
-    return (e4 < 2e-6 && e8 < 2e-6 && e16 < 4e-6) ? 0 : 1;
+    double e2 = check<2>(), e4 = check<4>(), e8 = check<8>(), e16 = check<16>(), e64 = check<64>();
+    printf("dft2 %.3e dft4 %.3e dft8 %.3e dft16 %.3e dft64 %.3e\n", e2, e4, e8, e16, e64);
+    return (e2 < 1e-6 && e4 < 2e-6 && e8 < 2e-6 && e16 < 4e-6 && e64 < 4e-6) ? 0 : 1;
 }

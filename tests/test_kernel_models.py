@@ -20,17 +20,3 @@ def test_model_reproduces_rfft(model):
                        cwd=os.path.join(ROOT, "tools"))
     assert r.returncode == 0, r.stdout + r.stderr
 
-
-def test_register_butterflies_on_the_host(tmp_path):
-    """Dft<2|4|8|16|64>::run are __host__ __device__: the code the kernels unroll, compiled for the CPU by nvcc and
-    compared with a direct f64 DFT (tests/cpp/test_dft_host.cu)."""
-    import shutil
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    if not os.path.exists(nvcc):
-        pytest.skip("nvcc not found")
-    exe = str(tmp_path / "test_dft_host")
-    subprocess.run([nvcc, "-std=c++17", "--expt-relaxed-constexpr", "-o", exe,
-                    os.path.join(ROOT, "tests", "cpp", "test_dft_host.cu")], check=True, capture_output=True)
-    r = subprocess.run([exe], capture_output=True, text=True)
-    assert r.returncode == 0, r.stdout
-    assert "radix 64" in r.stdout
