@@ -222,6 +222,54 @@ KOPEK_API kopek_status kopek_fft_large_c2c_f32(const float *d_in, float *d_out, 
 KOPEK_API kopek_status kopek_fft_dist_combine(const float *const *d_spectra, uint32_t ranks, uint32_t rank,
                                               uint64_t local_n, float *d_out, int device, void *cuda_stream);
 
+/* ---- 4. multi-GPU in ONE process: frames sharded over R devices, optional gather to devices[0] -----------------
+ * (what a Rust host links against -- no torch, no Python, one thread of the caller.)
+ * The reference's fft is a pure function of one frame (src/fft.rs:6), so frames shard with NO data-path collective:
+ * device r of R owns frames [floor(r F / R), floor((r + 1) F / R)) of the F = 1 + (n_samples - n) / hop frames of a
+ * buffer and reads samples [f0 * hop, (f1 - 1) * hop + n) -- neighbours both read the (n - hop)-sample halo.
+ * kopek_mgpu_shard reports those ranges; plan parameters are those of kopek_plan_create, one plan per device.
+ *
+ * kopek_mgpu_exec          device-resident shards: d_samples[r] / n_samples[r] / d_out[r] live on devices[r]; the R
+ *                          launches are enqueued on the context's per-device streams and the call returns.
+ * kopek_mgpu_exec_gathered same, but every device's kernel stores its rows straight INTO d_dst on devices[0] (rows in
+ *                          rank order, pitch = kopek_mgpu_out_pitch) through the peer mapping: transform and transfer
+ *                          are one kernel.  n = 1024 plans with f32 spectra and out_pitch_elems % 4 == 0 (e.g. 516)
+ *                          use the 2048-byte bulk-store epilogue, which is what reaches NVLink bandwidth.
+ * kopek_mgpu_gather        collects already computed shards (d_out[r], n_frames[r] rows each) into d_dst on devices[0]:
+ *                          KOPEK_GATHER_COPY = copy-engine peer copies pushed by the source devices' streams,
+ *                          KOPEK_GATHER_NCCL = one grouped ncclSend/ncclRecv (libnccl.so.2 is opened at run time;
+ *                          KOPEK_ERR_UNSUPPORTED if it is not installed).
+ * kopek_mgpu_sync          waits for everything enqueued so far; *elapsed_ms_max (may be NULL) = device time from the
+ *                          first enqueue since the previous sync to the last, maximum over the devices (CUDA events).
+ * kopek_mgpu_exec_host     ONE host buffer in, ONE host spectrogram out ([F][pitch]): the library splits the frame
+ *                          ranges and runs each device's chunked H2D -> kernel -> D2H pipeline from its own host
+ *                          thread; blocking.  Results are bit-identical to the one-device call (same kernels, same
+ *                          frames).  Pinned buffers (kopek_host_alloc) make the copies asynchronous. */
+typedef struct kopek_mgpu kopek_mgpu;
+enum { KOPEK_GATHER_COPY = 0, KOPEK_GATHER_NCCL = 1 };
+KOPEK_API kopek_status kopek_mgpu_create(kopek_mgpu **ctx, const int32_t *devices, uint32_t n_devices, uint32_t n,
+                                         uint32_t hop, uint32_t window, uint32_t output, uint32_t bins,
+                                         uint64_t out_pitch_elems);
+KOPEK_API kopek_status kopek_mgpu_destroy(kopek_mgpu *ctx);
+KOPEK_API uint32_t kopek_mgpu_device_count(const kopek_mgpu *ctx);
+KOPEK_API uint64_t kopek_mgpu_bins(const kopek_mgpu *ctx);
+KOPEK_API uint64_t kopek_mgpu_out_pitch(const kopek_mgpu *ctx);
+KOPEK_API uint64_t kopek_mgpu_out_elem_bytes(const kopek_mgpu *ctx);
+/* KOPEK_WINDOW_CUSTOM contexts: n coefficients (host pointer) for every device's plan */
+KOPEK_API kopek_status kopek_mgpu_set_custom_window(kopek_mgpu *ctx, const float *window_host);
+KOPEK_API kopek_status kopek_mgpu_shard(const kopek_mgpu *ctx, uint64_t n_samples, uint32_t rank,
+                                        uint64_t *sample_begin, uint64_t *sample_count, uint64_t *frame_begin,
+                                        uint64_t *frame_count);
+KOPEK_API kopek_status kopek_mgpu_exec(kopek_mgpu *ctx, const float *const *d_samples, const uint64_t *n_samples,
+                                       void *const *d_out, uint64_t *n_frames_out /* R entries, may be NULL */);
+KOPEK_API kopek_status kopek_mgpu_exec_gathered(kopek_mgpu *ctx, const float *const *d_samples,
+                                                const uint64_t *n_samples, void *d_dst, uint64_t *n_frames_total);
+KOPEK_API kopek_status kopek_mgpu_gather(kopek_mgpu *ctx, void *const *d_out, const uint64_t *n_frames, void *d_dst,
+                                         uint32_t mode);
+KOPEK_API kopek_status kopek_mgpu_sync(kopek_mgpu *ctx, float *elapsed_ms_max);
+KOPEK_API kopek_status kopek_mgpu_exec_host(kopek_mgpu *ctx, const float *h_samples, uint64_t n_samples, void *h_out,
+                                            uint64_t *n_frames_out);
+
 #ifdef __cplusplus
 }
 #endif

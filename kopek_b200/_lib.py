@@ -65,7 +65,21 @@ SYMBOLS = {
     "kopek_host_alloc": (_i32, [C.POINTER(_vp), _sz]),
     "kopek_host_free": (_i32, [_vp]),
     "kopek_fft_large_c2c_f32": (_i32, [_vp, _vp, _u64, C.c_int, _vp]),
+    "kopek_mgpu_create": (_i32, [C.POINTER(_vp), _vp, _u32, _u32, _u32, _u32, _u32, _u32, _u64]),
+    "kopek_mgpu_destroy": (_i32, [_vp]),
+    "kopek_mgpu_device_count": (_u32, [_vp]),
+    "kopek_mgpu_bins": (_u64, [_vp]),
+    "kopek_mgpu_out_pitch": (_u64, [_vp]),
+    "kopek_mgpu_out_elem_bytes": (_u64, [_vp]),
+    "kopek_mgpu_set_custom_window": (_i32, [_vp, _vp]),
+    "kopek_mgpu_shard": (_i32, [_vp, _u64, _u32, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
+    "kopek_mgpu_exec": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "kopek_mgpu_exec_gathered": (_i32, [_vp, _vp, _vp, _vp, C.POINTER(_u64)]),
+    "kopek_mgpu_gather": (_i32, [_vp, _vp, _vp, _vp, _u32]),
+    "kopek_mgpu_sync": (_i32, [_vp, C.POINTER(C.c_float)]),
+    "kopek_mgpu_exec_host": (_i32, [_vp, _vp, _u64, _vp, C.POINTER(_u64)]),
 }
+GATHER_COPY, GATHER_NCCL = 0, 1
 
 
 class KopekError(RuntimeError):

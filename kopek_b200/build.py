@@ -11,6 +11,7 @@ the GPU box with the repo snapshot.
 from __future__ import annotations
 
 import concurrent.futures as cf
+import hashlib
 import os
 import shutil
 import subprocess
@@ -41,11 +42,26 @@ def _sources():
     return srcs
 
 
-def _stale(target: str) -> bool:
+def _fingerprint(extra) -> str:
+    """Content hash of every source + the flags: the library is rebuilt exactly when one of them changed.  (Modification
+    times do not survive the snapshot that ships the tree to the GPU box; the stamp file next to the .so does.)"""
+    h = hashlib.sha256()
+    for path in _sources():
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join([*ARCH, *COMMON[:-1], *extra]).encode())
+    return h.hexdigest()
+
+
+def _stale(target: str, stamp: str) -> bool:
     if not os.path.exists(target):
         return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(s) > t for s in _sources())
+    try:
+        with open(target + ".stamp") as f:
+            return f.read().strip() != stamp
+    except OSError:
+        return True
 
 
 def _run(cmd, verbose):
@@ -64,29 +80,33 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False, 
     if tag:
         OBJ = os.path.join(HERE, "lib", "tune", tag, "obj")
         LIB = os.path.join(HERE, "lib", "tune", tag, "libkopek_cuda.so")
-    if not force and not _stale(LIB):
-        return LIB
-    os.makedirs(OBJ, exist_ok=True)
-    cc = nvcc()
-    extra = ["-Xptxas", "-v"] if ptxas_info else []
-    extra += list(defs)
+    extra = list(defs)
     if os.environ.get("KOPEK_K1_PREF") is not None:   # tuning: force the K1 register prefetch on/off for every size
         extra.append("-DK1_PREF_ALL=" + ("true" if os.environ["KOPEK_K1_PREF"] == "1" else "false"))
     if os.environ.get("KOPEK_K1W_SWEEP"):      # build every K1W tuning variant (tools/sweep_k1w.py)
         extra.append("-DKOPEK_K1W_SWEEP")
+    stamp = _fingerprint(extra)
+    if not force and not ptxas_info and not _stale(LIB, stamp):
+        return LIB
+    os.makedirs(OBJ, exist_ok=True)
+    cc = nvcc()
+    if ptxas_info:
+        extra = ["-Xptxas", "-v", *extra]
     jobs = []
     for n in K1_SIZES:
         obj = os.path.join(OBJ, f"k1_{n}.o")
         jobs.append((obj, [cc, *ARCH, *COMMON, *extra, f"-DKOPEK_K1_N={n}", "-c", os.path.join(CSRC, "k1_inst.cu"),
                            "-o", obj]))
-    for name in ("kopek_cuda", "k1w_inst", "k1m_inst", "fft_large", "synth", "pcm", "dist_fft"):
+    for name in ("kopek_cuda", "k1w_inst", "k1m_inst", "fft_large", "synth", "pcm", "dist_fft", "mgpu"):
         src = os.path.join(CSRC, name + ".cu")
         if os.path.exists(src):
             obj = os.path.join(OBJ, name + ".o")
             jobs.append((obj, [cc, *ARCH, *COMMON, *extra, "-c", src, "-o", obj]))
     with cf.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
         list(ex.map(lambda j: _run(j[1], verbose or ptxas_info), jobs))
-    _run([cc, *ARCH, "-shared", "-cudart", "static", "-o", LIB, *[j[0] for j in jobs]], verbose)
+    _run([cc, *ARCH, "-shared", "-cudart", "static", "-o", LIB, *[j[0] for j in jobs], "-ldl"], verbose)
+    with open(LIB + ".stamp", "w") as f:
+        f.write(stamp + "\n")
     return LIB
 
 

@@ -378,11 +378,35 @@ struct K3Plan {
     uint64_t n = 0;
     int device = -1;
     int n1 = 0, n2 = 0;
-    float2 *tw1 = nullptr, *tw2 = nullptr, *hi = nullptr, *lo = nullptr, *mid = nullptr;
+    float2 *tw1 = nullptr, *tw2 = nullptr, *hi = nullptr, *lo = nullptr;
     float2 *tw2r = nullptr;    // N2 = 4096: stage table of the two-stage radix-64 pass 2
 };
+// Tables only: one entry per (n, device), at most 9 lengths per device, kept for the life of the process, so a plan
+// handed out under the lock stays valid however many threads and streams call in.  The pass-1 -> pass-2 workspace
+// `mid` is NOT part of the plan: it is allocated per call, stream-ordered on the caller's stream, from a per-device
+// pool that keeps its memory between calls (k3_workspace_pool) -- two calls on different streams never share it.
 static std::mutex g_k3_mu;
 static std::vector<K3Plan> g_k3_plans;
+static cudaMemPool_t g_k3_pool[64];
+
+static kopek_status k3_workspace_pool(int device, cudaMemPool_t *out) {
+    if (device < 0 || device >= 64) return fail(KOPEK_ERR_INVALID, "device %d out of range", device);
+    std::lock_guard<std::mutex> lk(g_k3_mu);
+    if (!g_k3_pool[device]) {
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaMemPool_t pool = nullptr;
+        KOPEK_CUDA(cudaMemPoolCreate(&pool, &props));
+        uint64_t keep = ~0ull;                    // never trim at synchronisation points: the next call reuses the block
+        KOPEK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        g_k3_pool[device] = pool;
+    }
+    *out = g_k3_pool[device];
+    return KOPEK_OK;
+}
 
 // Stage tables of the M-point Stockham sub-transform: block s holds tw[(t-1) NS + kk] = W_{NS RAD}^{kk t}.
 template <int M> static void stage_twiddles_t(std::vector<float2> &v) {
@@ -446,17 +470,10 @@ static kopek_status k3_get_plan(uint64_t n, int device, K3Plan *out) {
                 t2r[(t - 1) * 64 + kk] = make_float2((float)cos(th), (float)sin(th));
             }
     }
-    if (!up(&p.tw1, t1) || !up(&p.tw2, t2) || !up(&p.hi, hi) || !up(&p.lo, lo) || (!t2r.empty() && !up(&p.tw2r, t2r)) ||
-        cudaMalloc(&p.mid, n * sizeof(float2)) != cudaSuccess) {
-        cudaFree(p.tw1); cudaFree(p.tw2); cudaFree(p.hi); cudaFree(p.lo); cudaFree(p.mid); cudaFree(p.tw2r);
-        return fail(KOPEK_ERR_NOMEM, "four-step plan for n=%llu: %s", (unsigned long long)n,
+    if (!up(&p.tw1, t1) || !up(&p.tw2, t2) || !up(&p.hi, hi) || !up(&p.lo, lo) || (!t2r.empty() && !up(&p.tw2r, t2r))) {
+        cudaFree(p.tw1); cudaFree(p.tw2); cudaFree(p.hi); cudaFree(p.lo); cudaFree(p.tw2r);
+        return fail(KOPEK_ERR_NOMEM, "four-step tables for n=%llu: %s", (unsigned long long)n,
                     cudaGetErrorString(cudaGetLastError()));
-    }
-    if (g_k3_plans.size() >= 4) {       // keep the cache (and its n-sized workspaces) small
-        cudaDeviceSynchronize();
-        K3Plan &o = g_k3_plans.front();
-        cudaFree(o.tw1); cudaFree(o.tw2); cudaFree(o.hi); cudaFree(o.lo); cudaFree(o.mid); cudaFree(o.tw2r);
-        g_k3_plans.erase(g_k3_plans.begin());
     }
     g_k3_plans.push_back(p);
     *out = p;
@@ -515,32 +532,46 @@ extern "C" kopek_status kopek_fft_large_c2c_f32(const float *d_in, float *d_out,
     cudaStream_t stream = (cudaStream_t)cuda_stream;
     int sms = 0;
     KOPEK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    cudaError_t e = cudaErrorInvalidValue;
+    // workspace between the passes: this call's own, ordered on the caller's stream (allocation, both passes, release)
+    cudaMemPool_t pool = nullptr;
+    if ((st = k3_workspace_pool(device, &pool)) != KOPEK_OK) return st;
+    float2 *mid = nullptr;
+    cudaError_t e = cudaMallocFromPoolAsync(reinterpret_cast<void **>(&mid), n * sizeof(float2), pool, stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(KOPEK_ERR_NOMEM, "four-step workspace of %llu bytes: %s", (unsigned long long)(n * sizeof(float2)),
+                    cudaGetErrorString(e));
+    }
+    struct Release {           // every exit path hands the block back in stream order
+        float2 *ptr; cudaStream_t s;
+        ~Release() { cudaFreeAsync(ptr, s); }
+    } release{mid, stream};
+    e = cudaErrorInvalidValue;
     switch (p.n1) {
-        case 256: e = launch_pass1<256>(p.n2 / 2, sms, in_map, p.mid, tb, stream); break;
-        case 512: e = launch_pass1<512>(p.n2 / 2, sms, in_map, p.mid, tb, stream); break;
-        case 1024: e = launch_pass1<1024>(p.n2 / 2, sms, in_map, p.mid, tb, stream); break;
-        case 2048: e = launch_pass1<2048>(p.n2 / 2, sms, in_map, p.mid, tb, stream); break;
-        case 4096: e = launch_pass1<4096>(p.n2 / 2, sms, in_map, p.mid, tb, stream); break;
+        case 256: e = launch_pass1<256>(p.n2 / 2, sms, in_map, mid, tb, stream); break;
+        case 512: e = launch_pass1<512>(p.n2 / 2, sms, in_map, mid, tb, stream); break;
+        case 1024: e = launch_pass1<1024>(p.n2 / 2, sms, in_map, mid, tb, stream); break;
+        case 2048: e = launch_pass1<2048>(p.n2 / 2, sms, in_map, mid, tb, stream); break;
+        case 4096: e = launch_pass1<4096>(p.n2 / 2, sms, in_map, mid, tb, stream); break;
     }
     if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "four-step pass 1 (N1=%d): %s", p.n1, cudaGetErrorString(e));
     switch (p.n2) {
-        case 256: e = launch_pass2<256>(p.n1 / 4, sms, p.mid, reinterpret_cast<float2 *>(d_out), tb, stream); break;
-        case 512: e = launch_pass2<512>(p.n1 / 4, sms, p.mid, reinterpret_cast<float2 *>(d_out), tb, stream); break;
-        case 1024: e = launch_pass2<1024>(p.n1 / 4, sms, p.mid, reinterpret_cast<float2 *>(d_out), tb, stream); break;
-        case 2048: e = launch_pass2<2048>(p.n1 / 4, sms, p.mid, reinterpret_cast<float2 *>(d_out), tb, stream); break;
+        case 256: e = launch_pass2<256>(p.n1 / 4, sms, mid, reinterpret_cast<float2 *>(d_out), tb, stream); break;
+        case 512: e = launch_pass2<512>(p.n1 / 4, sms, mid, reinterpret_cast<float2 *>(d_out), tb, stream); break;
+        case 1024: e = launch_pass2<1024>(p.n1 / 4, sms, mid, reinterpret_cast<float2 *>(d_out), tb, stream); break;
+        case 2048: e = launch_pass2<2048>(p.n1 / 4, sms, mid, reinterpret_cast<float2 *>(d_out), tb, stream); break;
         case 4096: {
             static const bool r64 = !(getenv("KOPEK_K3_R64") && atoi(getenv("KOPEK_K3_R64")) == 0);   // tuning switch
             if (r64) {
                 const int tiles = p.n1 / 4;
                 e = cudaFuncSetAttribute(k3_pass2_r64, cudaFuncAttributeMaxDynamicSharedMemorySize, K3R_SMEM);
                 if (e == cudaSuccess) {
-                    k3_pass2_r64<<<tiles < sms ? tiles : sms, 256, K3R_SMEM, stream>>>(p.mid, reinterpret_cast<float2 *>(d_out),
+                    k3_pass2_r64<<<tiles < sms ? tiles : sms, 256, K3R_SMEM, stream>>>(mid, reinterpret_cast<float2 *>(d_out),
                                                                                      p.tw2r, tiles);
                     e = cudaGetLastError();
                 }
             } else {
-                e = launch_pass2<4096>(p.n1 / 4, sms, p.mid, reinterpret_cast<float2 *>(d_out), tb, stream);
+                e = launch_pass2<4096>(p.n1 / 4, sms, mid, reinterpret_cast<float2 *>(d_out), tb, stream);
             }
             break;
         }

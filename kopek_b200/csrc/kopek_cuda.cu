@@ -64,7 +64,7 @@ struct K2Context {
 };
 static K2Context g_k2;
 static std::mutex g_tw_mu;
-static std::vector<TwiddleTable> g_tw_tables;   // small LRU, most recent last
+static std::vector<TwiddleTable> g_tw_tables;   // one table per (n, device), kept for the life of the process
 
 constexpr int K2_CHUNK_LOG_MAX = 12;       // 4096 complex f64 = 64 KiB of shared memory
 constexpr size_t K2_PINNED_MAX = 8u << 20; // staging through pinned memory up to 8 MiB
@@ -77,10 +77,7 @@ static kopek_status k2_get_twiddles(size_t n, int device, const double2 **out) {
     std::lock_guard<std::mutex> lk(g_tw_mu);
     for (size_t t = 0; t < g_tw_tables.size(); ++t)
         if (g_tw_tables[t].n == n && g_tw_tables[t].device == device) {
-            TwiddleTable hit = g_tw_tables[t];
-            g_tw_tables.erase(g_tw_tables.begin() + t);
-            g_tw_tables.push_back(hit);
-            *out = hit.d;
+            *out = g_tw_tables[t].d;
             return KOPEK_OK;
         }
     size_t cnt = n / 2 ? n / 2 : 1;
@@ -100,13 +97,8 @@ static kopek_status k2_get_twiddles(size_t n, int device, const double2 **out) {
         cudaFree(tb.d);
         return fail(KOPEK_ERR_CUDA, "twiddle upload failed: %s", cudaGetErrorString(e));
     }
-    if (g_tw_tables.size() >= 8) {   // evict least recently used
-        // the evicted table may still be read by a kernel in flight on some stream
-        DeviceGuard ge(g_tw_tables.front().device);
-        cudaDeviceSynchronize();
-        cudaFree(g_tw_tables.front().d);
-        g_tw_tables.erase(g_tw_tables.begin());
-    }
+    // never evicted: a caller may still be about to launch on a table handed out earlier, and there are at most
+    // 31 power-of-two lengths per device (2^30 points = 8 GiB of twiddles only if someone really transforms 2^30)
     g_tw_tables.push_back(tb);
     *out = tb.d;
     return KOPEK_OK;
@@ -859,61 +851,90 @@ kopek_status kopek_stft_exec_host(kopek_plan *plan, const float *h_samples, uint
     DeviceGuard g(plan->device);
     if (!g.ok) return fail(KOPEK_ERR_CUDA, "cannot select device %d", plan->device);
 
-    // chunk so that one slot moves ~KOPEK_HOST_CHUNK_MB MiB of samples; three slots keep the H2D engine, the SMs
-    // and the D2H engine busy at the same time.  The first upload and the last download are not overlapped with
-    // anything, so the chunk is kept small against the call (measured on B200, tools/sweep_host_chunk.py).
+    // chunk so that one slot moves ~KOPEK_HOST_CHUNK_MB MiB over its busier direction (samples in, or spectra out when
+    // frames overlap: hop = 1, n = 4096 writes 8 KB per 4 bytes read); three slots keep the H2D engine, the SMs and
+    // the D2H engine busy at the same time.  The first upload and the last download are not overlapped with anything,
+    // so the chunk is kept small against the call (measured on B200, tools/sweep_host_chunk.py).
     const uint64_t n = plan->n, hop = plan->hop;
     uint64_t chunk_mb = K1_HOST_CHUNK_MB;
     if (const char *env = getenv("KOPEK_HOST_CHUNK_MB")) chunk_mb = std::max(1, atoi(env));
-    uint64_t cf = std::max<uint64_t>(1, (chunk_mb << 20) / (hop * sizeof(float)));
+    const uint64_t per_frame = std::max<uint64_t>(hop * sizeof(float), plan->pitch * plan->elem_bytes);
+    uint64_t cf = std::max<uint64_t>(1, (chunk_mb << 20) / per_frame);
     cf = std::min(cf, frames);
     const uint64_t in_elems = (cf - 1) * hop + n;
     const uint64_t out_bytes = cf * plan->pitch * plan->elem_bytes;
     if (plan->slot_frames < cf) {
+        cudaError_t e = cudaSuccess;
         for (HostSlot &s : plan->slots) {
             if (s.d_in) cudaFree(s.d_in);
             if (s.d_out) cudaFree(s.d_out);
             s.d_in = nullptr; s.d_out = nullptr;
-            if (!s.stream) KOPEK_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-            KOPEK_CUDA(cudaMalloc(&s.d_in, in_elems * sizeof(float)));
-            KOPEK_CUDA(cudaMalloc(&s.d_out, out_bytes));
+        }
+        plan->slot_frames = 0;
+        for (HostSlot &s : plan->slots) {
+            if (!s.stream && (e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess) break;
+            if ((e = cudaMalloc(&s.d_in, in_elems * sizeof(float))) != cudaSuccess) break;
+            if ((e = cudaMalloc(&s.d_out, out_bytes)) != cudaSuccess) break;
+        }
+        if (e != cudaSuccess) {          // all or nothing: a later call must not find half-sized slots
+            for (HostSlot &s : plan->slots) {
+                if (s.d_in) cudaFree(s.d_in);
+                if (s.d_out) cudaFree(s.d_out);
+                s.d_in = nullptr; s.d_out = nullptr;
+            }
+            cudaGetLastError();
+            return fail(KOPEK_ERR_NOMEM, "chunk slots (%llu frames each): %s", (unsigned long long)cf, cudaGetErrorString(e));
         }
         plan->slot_frames = cf;
     }
+    // fault injection for tests/test_gpu_guards.py: fail the enqueue of chunk K (0-based) as a launch failure would
+    long fail_chunk = -1;
+    if (const char *env = getenv("KOPEK_TEST_FAIL_CHUNK")) fail_chunk = atol(env);
     uint32_t launches = 0;
     uint64_t c = 0;
-    for (uint64_t f0 = 0; f0 < frames; f0 += cf, ++c) {
+    kopek_status st = KOPEK_OK;
+    for (uint64_t f0 = 0; f0 < frames && st == KOPEK_OK; f0 += cf, ++c) {
         HostSlot &s = plan->slots[c % 3];
         const uint64_t nf = std::min(cf, frames - f0);
         const uint64_t ne = (nf - 1) * hop + n;
-        KOPEK_CUDA(cudaMemcpyAsync(s.d_in, h_samples + f0 * hop, ne * sizeof(float), cudaMemcpyHostToDevice, s.stream));
-        kopek_status st = stft_launch(plan, s.d_in, nf, s.d_out, s.stream);
-        if (st != KOPEK_OK) return st;
+        cudaError_t e = cudaMemcpyAsync(s.d_in, h_samples + f0 * hop, ne * sizeof(float), cudaMemcpyHostToDevice, s.stream);
+        if (e != cudaSuccess) { st = fail(KOPEK_ERR_CUDA, "chunk %llu upload: %s", (unsigned long long)c, cudaGetErrorString(e)); break; }
+        if ((long)c == fail_chunk) { st = fail(KOPEK_ERR_CUDA, "chunk %llu: injected launch failure", (unsigned long long)c); break; }
+        st = stft_launch(plan, s.d_in, nf, s.d_out, s.stream);
+        if (st != KOPEK_OK) break;
         ++launches;
         // rows are contiguous (pitch) so one copy returns the chunk; the tail of the
         // last row beyond `bins` is unspecified padding when pitch > bins
         const uint64_t ob = ((nf - 1) * plan->pitch + plan->bins) * plan->elem_bytes;
-        KOPEK_CUDA(cudaMemcpyAsync((char *)h_out + f0 * plan->pitch * plan->elem_bytes, s.d_out, ob,
-                                   cudaMemcpyDeviceToHost, s.stream));
+        e = cudaMemcpyAsync((char *)h_out + f0 * plan->pitch * plan->elem_bytes, s.d_out, ob, cudaMemcpyDeviceToHost, s.stream);
+        if (e != cudaSuccess) st = fail(KOPEK_ERR_CUDA, "chunk %llu download: %s", (unsigned long long)c, cudaGetErrorString(e));
     }
-    for (HostSlot &s : plan->slots)
-        if (s.stream) KOPEK_CUDA(cudaStreamSynchronize(s.stream));
+    // drain EVERY slot stream, also on the error path: chunks enqueued before the failure are still copying into the
+    // caller's h_out, which the caller is free to release as soon as this call returns
+    for (HostSlot &s : plan->slots) {
+        if (!s.stream) continue;
+        cudaError_t e = cudaStreamSynchronize(s.stream);
+        if (e != cudaSuccess && st == KOPEK_OK) st = fail(KOPEK_ERR_CUDA, "chunk pipeline: %s", cudaGetErrorString(e));
+    }
     plan->last_launches = launches;
-    return KOPEK_OK;
+    return st;
 }
 
 // ------------------------------------------------------------- live stream ----
 // The beep view's sliding VecDeque of the last n samples (examples/beep/view.rs:44,57-60).  A push is a latency
-// path (a few KB per UI frame), so nothing is copied by DMA: the doubled ring and the spectrum live in MAPPED pinned
-// host memory, the plan's kernel reads the latest n samples from the ring over PCIe (in order) and stores the
-// spectrum straight back -- one launch and one stream synchronisation per push.
+// path (a few KB per UI frame), so nothing is copied by DMA: the window and the spectrum live in MAPPED pinned
+// host memory, the plan's kernel reads the n samples over PCIe (in order) and stores the spectrum straight back --
+// one launch and one stream synchronisation per push.  The ring itself is ordinary host memory; every push
+// linearises the latest n samples into the mapped, 256-byte aligned window (two memcpys, <= 16 KB), so the kernel
+// always sees an aligned frame: the same (fast) kernel, the same rounding, whatever the push sizes add up to.
 struct kopek_stream {
     kopek_plan *plan;
     uint32_t n;
     int device;
     uint64_t written;          // total samples pushed so far
-    float *h_ring;             // mapped pinned, 2n floats: sample i lives at i % n and i % n + n
-    float *d_ring;             // the device's address of h_ring
+    float *h_ring;             // host ring of n floats: sample i lives at i % n
+    float *h_win;              // mapped pinned, n floats: the latest n samples in order (rebuilt by every push)
+    float *d_win;              // the device's address of h_win
     void *h_out;               // mapped pinned, one spectrum
     void *d_out;               // the device's address of h_out
     cudaStream_t cs;
@@ -941,19 +962,20 @@ kopek_status kopek_stream_create(kopek_stream **stream, uint32_t n, uint32_t win
     kopek_stream *s = new (std::nothrow) kopek_stream();
     if (!s) { kopek_plan_destroy(plan); return fail(KOPEK_ERR_NOMEM, "out of host memory"); }
     s->plan = plan; s->n = n; s->device = device; s->written = 0;
-    s->h_ring = nullptr; s->d_ring = nullptr; s->h_out = nullptr; s->d_out = nullptr; s->cs = nullptr;
+    s->h_ring = nullptr; s->h_win = nullptr; s->d_win = nullptr; s->h_out = nullptr; s->d_out = nullptr; s->cs = nullptr;
     DeviceGuard g(device);
     const size_t ob = plan->bins * plan->elem_bytes;
     cudaError_t e;
-    if ((e = cudaHostAlloc(&s->h_ring, 2 * n * sizeof(float), cudaHostAllocMapped)) != cudaSuccess ||
-        (e = cudaHostGetDevicePointer(&s->d_ring, s->h_ring, 0)) != cudaSuccess ||
+    s->h_ring = static_cast<float *>(calloc(n, sizeof(float)));      // the VecDeque starts as n zeros
+    if (!s->h_ring) { kopek_stream_destroy(s); return fail(KOPEK_ERR_NOMEM, "out of host memory"); }
+    if ((e = cudaHostAlloc(&s->h_win, n * sizeof(float), cudaHostAllocMapped)) != cudaSuccess ||
+        (e = cudaHostGetDevicePointer(&s->d_win, s->h_win, 0)) != cudaSuccess ||
         (e = cudaHostAlloc(&s->h_out, ob, cudaHostAllocMapped)) != cudaSuccess ||
         (e = cudaHostGetDevicePointer(&s->d_out, s->h_out, 0)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&s->cs, cudaStreamNonBlocking)) != cudaSuccess) {
         kopek_stream_destroy(s);
         return fail(KOPEK_ERR_CUDA, "stream setup failed: %s", cudaGetErrorString(e));
     }
-    memset(s->h_ring, 0, 2 * n * sizeof(float));      // the VecDeque starts as n zeros
     *stream = s;
     return KOPEK_OK;
 }
@@ -973,18 +995,20 @@ kopek_status kopek_stream_push(kopek_stream *s, const float *h_samples, uint32_t
     }
     if (count) {
         uint32_t pos = (uint32_t)(s->written % n), done = 0;
-        while (done < count) {             // at most two segments (wrap), each written to both ring halves
+        while (done < count) {             // at most two segments (wrap)
             uint32_t seg = std::min(count - done, n - pos);
             memcpy(s->h_ring + pos, h_samples + done, seg * sizeof(float));
-            memcpy(s->h_ring + pos + n, h_samples + done, seg * sizeof(float));
             done += seg;
             pos = (pos + seg) % n;
         }
         s->written += count;
     }
-    // the most recent n samples are contiguous from (written % n) in the doubled ring; the launch orders the host's
-    // writes before the kernel's reads, the synchronisation orders the kernel's stores before the host's reads
-    const float *frame = s->d_ring + (s->written % n);
+    // the most recent n samples start at (written % n) in the ring: linearise them into the mapped window; the launch
+    // orders the host's writes before the kernel's reads, the synchronisation the kernel's stores before the host's reads
+    const uint32_t head = (uint32_t)(s->written % n);
+    memcpy(s->h_win, s->h_ring + head, (n - head) * sizeof(float));
+    if (head) memcpy(s->h_win + (n - head), s->h_ring, head * sizeof(float));
+    const float *frame = s->d_win;
     uint64_t nf = 0;
     kopek_status st = kopek_stft_exec(s->plan, frame, n, s->d_out, &nf, s->cs);
     if (st != KOPEK_OK) return st;
@@ -997,7 +1021,8 @@ kopek_status kopek_stream_destroy(kopek_stream *s) {
     if (!s) return KOPEK_OK;
     DeviceGuard g(s->device);
     if (s->cs) { cudaStreamSynchronize(s->cs); cudaStreamDestroy(s->cs); }
-    if (s->h_ring) cudaFreeHost(s->h_ring);
+    free(s->h_ring);
+    if (s->h_win) cudaFreeHost(s->h_win);
     if (s->h_out) cudaFreeHost(s->h_out);
     if (s->plan) kopek_plan_destroy(s->plan);
     delete s;

@@ -203,3 +203,95 @@ class DistributedFFT:
         if self._own:
             self._lib.kopek_device_free(self._own, self.device)
             self._own = self._C.c_void_p()
+
+
+# ---- one process, R devices: the C ABI's own multi-GPU entry points (include/kopek_cuda.h section 4) ---------------
+class MultiGpuStft:
+    """kopek_mgpu_*: frames of one buffer sharded over `devices` from ONE process, no torch on the data path.
+
+    `exec_host(samples)` is the call a reference-side caller makes (host buffer in, [frames, bins] spectrogram out);
+    `exec_ptrs` / `exec_gathered_ptr` / `gather_ptrs` work on device pointers; `sync()` returns the device time (ms,
+    max over the devices) of everything enqueued since the previous sync."""
+
+    def __init__(self, devices, n: int, hop: int | None = None, window: int = 0, output: int = 1, bins: int = 0,
+                 out_pitch: int = 0):
+        import ctypes as C
+
+        from . import _lib
+        self._C, self._lib, self._check = C, _lib.load(), _lib.check
+        self.devices = [int(d) for d in devices]
+        self.n, self.hop = n, (n if hop is None else hop)
+        self._h = C.c_void_p()
+        arr = (C.c_int32 * len(self.devices))(*self.devices)
+        self._check(self._lib.kopek_mgpu_create(C.byref(self._h), arr, len(self.devices), n, self.hop, window, output,
+                                                bins, out_pitch))
+        self.bins = int(self._lib.kopek_mgpu_bins(self._h))
+        self.pitch = int(self._lib.kopek_mgpu_out_pitch(self._h))
+        self.elem_bytes = int(self._lib.kopek_mgpu_out_elem_bytes(self._h))
+
+    def frames(self, n_samples: int) -> int:
+        return 0 if n_samples < self.n else 1 + (n_samples - self.n) // self.hop
+
+    def shard(self, n_samples: int, rank: int):
+        """(sample_begin, sample_count, frame_begin, frame_count) of device `rank`."""
+        C = self._C
+        v = [C.c_uint64(0) for _ in range(4)]
+        self._check(self._lib.kopek_mgpu_shard(self._h, n_samples, rank, *[C.byref(x) for x in v]))
+        return tuple(int(x.value) for x in v)
+
+    def _ptr_array(self, ptrs):
+        return (self._C.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+
+    def _u64_array(self, vals):
+        return (self._C.c_uint64 * len(vals))(*[int(v) for v in vals])
+
+    def exec_ptrs(self, d_samples, n_samples, d_out):
+        got = self._u64_array([0] * len(self.devices))
+        self._check(self._lib.kopek_mgpu_exec(self._h, self._ptr_array(d_samples), self._u64_array(n_samples),
+                                              self._ptr_array(d_out), got))
+        return [int(g) for g in got]
+
+    def exec_gathered_ptr(self, d_samples, n_samples, d_dst: int) -> int:
+        total = self._C.c_uint64(0)
+        self._check(self._lib.kopek_mgpu_exec_gathered(self._h, self._ptr_array(d_samples), self._u64_array(n_samples),
+                                                       d_dst, self._C.byref(total)))
+        return int(total.value)
+
+    def gather_ptrs(self, d_out, n_frames, d_dst: int, mode: int = 0) -> None:
+        self._check(self._lib.kopek_mgpu_gather(self._h, self._ptr_array(d_out), self._u64_array(n_frames), d_dst, mode))
+
+    def sync(self) -> float:
+        ms = self._C.c_float(0.0)
+        self._check(self._lib.kopek_mgpu_sync(self._h, self._C.byref(ms)))
+        return float(ms.value)
+
+    def exec_host_ptr(self, h_samples: int, n_samples: int, h_out: int) -> int:
+        nf = self._C.c_uint64(0)
+        self._check(self._lib.kopek_mgpu_exec_host(self._h, h_samples, n_samples, h_out, self._C.byref(nf)))
+        return int(nf.value)
+
+    def exec_host(self, samples):
+        import numpy as np
+        s = np.ascontiguousarray(samples, dtype=np.float32).reshape(-1)
+        frames = self.frames(s.size)
+        out = np.empty((frames, self.pitch), dtype=np.complex64 if self.elem_bytes == 8 else np.float32)
+        if frames:
+            self.exec_host_ptr(s.ctypes.data, s.size, out.ctypes.data)
+        return out[:, :self.bins]
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.kopek_mgpu_destroy(self._h)
+            self._h = self._C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

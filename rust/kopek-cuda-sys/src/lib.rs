@@ -35,6 +35,12 @@ pub struct kopek_plan {
 pub struct kopek_stream {
     _private: [u8; 0],
 }
+#[repr(C)]
+pub struct kopek_mgpu {
+    _private: [u8; 0],
+}
+pub const KOPEK_GATHER_COPY: u32 = 0;
+pub const KOPEK_GATHER_NCCL: u32 = 1;
 
 extern "C" {
     pub fn kopek_last_error() -> *const c_char;
@@ -97,4 +103,25 @@ extern "C" {
 
     pub fn kopek_fft_large_c2c_f32(d_in: *const f32, d_out: *mut f32, n: u64, device: c_int,
                                    cuda_stream: *mut c_void) -> kopek_status;
+
+    // ---- multi-GPU in one process (include/kopek_cuda.h section 4)
+    pub fn kopek_mgpu_create(ctx: *mut *mut kopek_mgpu, devices: *const i32, n_devices: u32, n: u32, hop: u32,
+                             window: u32, output: u32, bins: u32, out_pitch_elems: u64) -> kopek_status;
+    pub fn kopek_mgpu_destroy(ctx: *mut kopek_mgpu) -> kopek_status;
+    pub fn kopek_mgpu_device_count(ctx: *const kopek_mgpu) -> u32;
+    pub fn kopek_mgpu_bins(ctx: *const kopek_mgpu) -> u64;
+    pub fn kopek_mgpu_out_pitch(ctx: *const kopek_mgpu) -> u64;
+    pub fn kopek_mgpu_out_elem_bytes(ctx: *const kopek_mgpu) -> u64;
+    pub fn kopek_mgpu_set_custom_window(ctx: *mut kopek_mgpu, window_host: *const f32) -> kopek_status;
+    pub fn kopek_mgpu_shard(ctx: *const kopek_mgpu, n_samples: u64, rank: u32, sample_begin: *mut u64,
+                            sample_count: *mut u64, frame_begin: *mut u64, frame_count: *mut u64) -> kopek_status;
+    pub fn kopek_mgpu_exec(ctx: *mut kopek_mgpu, d_samples: *const *const f32, n_samples: *const u64,
+                           d_out: *const *mut c_void, n_frames_out: *mut u64) -> kopek_status;
+    pub fn kopek_mgpu_exec_gathered(ctx: *mut kopek_mgpu, d_samples: *const *const f32, n_samples: *const u64,
+                                    d_dst: *mut c_void, n_frames_total: *mut u64) -> kopek_status;
+    pub fn kopek_mgpu_gather(ctx: *mut kopek_mgpu, d_out: *const *mut c_void, n_frames: *const u64, d_dst: *mut c_void,
+                             mode: u32) -> kopek_status;
+    pub fn kopek_mgpu_sync(ctx: *mut kopek_mgpu, elapsed_ms_max: *mut f32) -> kopek_status;
+    pub fn kopek_mgpu_exec_host(ctx: *mut kopek_mgpu, h_samples: *const f32, n_samples: u64, h_out: *mut c_void,
+                                n_frames_out: *mut u64) -> kopek_status;
 }

@@ -33,26 +33,108 @@ pub fn show(label: &str, buf: &[Complex<f64>]) {
     }
 }
 
+/// A fused window -> real FFT -> epilogue plan (kopek_plan_*): device tables and the chunk slots of the host-buffer
+/// path live as long as the value, so a caller that analyses a stream of buffers builds it once.
+pub struct Plan {
+    raw: *mut sys::kopek_plan,
+    bins: usize,
+}
+// the C library serialises host-buffer executes of one plan behind its own mutex
+unsafe impl Send for Plan {}
+
+impl Plan {
+    pub fn new(n: u32, hop: u32, window: u32, output: u32, device: i32) -> Plan {
+        let mut raw: *mut sys::kopek_plan = std::ptr::null_mut();
+        let st = unsafe { sys::kopek_plan_create(&mut raw, n, hop, window, output, sys::KOPEK_BINS_HALF, 0, device) };
+        if st != sys::KOPEK_OK {
+            panic!("kopek::fft::Plan::new: {}", last_error());
+        }
+        let bins = unsafe { sys::kopek_plan_bins(raw) } as usize;
+        Plan { raw, bins }
+    }
+
+    pub fn bins(&self) -> usize {
+        self.bins
+    }
+
+    /// Host samples in, `frames x bins` f32 values out (row-major); copies happen inside the call.
+    pub fn exec(&mut self, samples: &[f32]) -> Vec<f32> {
+        let frames = unsafe { sys::kopek_plan_frames(self.raw, samples.len() as u64) } as usize;
+        let mut flat = vec![0f32; frames * self.bins];
+        let mut got = 0u64;
+        let st = unsafe {
+            sys::kopek_stft_exec_host(self.raw, samples.as_ptr(), samples.len() as u64, flat.as_mut_ptr() as *mut _, &mut got)
+        };
+        if st != sys::KOPEK_OK {
+            panic!("kopek::fft::Plan::exec: {}", last_error());
+        }
+        flat
+    }
+}
+
+impl Drop for Plan {
+    fn drop(&mut self) {
+        unsafe { sys::kopek_plan_destroy(self.raw) };
+    }
+}
+
+thread_local! {
+    // the few most recently used plans of this thread, keyed by (n, hop, window): a UI loop that calls
+    // stft_magnitude once per rendered frame pays for cudaMalloc and the table uploads once, not per call
+    static PLANS: std::cell::RefCell<Vec<((u32, u32, u32), Plan)>> = std::cell::RefCell::new(Vec::new());
+}
+const PLAN_CACHE: usize = 4;
+
 /// Batched analysis of many frames at once (what the three callers of `fft` -- examples/beep/view.rs:140-158,
 /// examples/graph/player.rs:56-61, examples/pong/main.rs:192-196 -- become when more than one frame is pending):
 /// window -> real FFT -> |X| in one fused kernel.  `samples` are f32 as the callers hold them.
 pub fn stft_magnitude(samples: &[f32], n: u32, hop: u32, hann: bool) -> Vec<Vec<f32>> {
-    let mut plan: *mut sys::kopek_plan = std::ptr::null_mut();
     let window = if hann { sys::KOPEK_WINDOW_HANN } else { sys::KOPEK_WINDOW_RECT };
-    let st = unsafe { sys::kopek_plan_create(&mut plan, n, hop, window, sys::KOPEK_OUT_MAG, sys::KOPEK_BINS_HALF, 0, 0) };
+    PLANS.with(|cell| {
+        let mut cache = cell.borrow_mut();
+        let key = (n, hop, window);
+        let at = match cache.iter().position(|(k, _)| *k == key) {
+            Some(i) => i,
+            None => {
+                if cache.len() >= PLAN_CACHE {
+                    cache.remove(0); // least recently used sits in front
+                }
+                cache.push((key, Plan::new(n, hop, window, sys::KOPEK_OUT_MAG, 0)));
+                cache.len() - 1
+            }
+        };
+        let entry = cache.remove(at);
+        cache.push(entry); // most recently used at the back
+        let plan = &mut cache.last_mut().unwrap().1;
+        let bins = plan.bins();
+        plan.exec(samples).chunks(bins).map(|r| r.to_vec()).collect()
+    })
+}
+
+/// The same analysis spread over several GPUs of this machine from ONE process (kopek_mgpu_*): the library splits the
+/// frame range, every device transforms its contiguous share (frames are independent, src/fft.rs:6 is a pure function)
+/// and the rows land at their final place in the result, bit-identical to the single-device call.
+pub fn stft_magnitude_multi(samples: &[f32], n: u32, hop: u32, hann: bool, devices: &[i32]) -> Vec<Vec<f32>> {
+    let window = if hann { sys::KOPEK_WINDOW_HANN } else { sys::KOPEK_WINDOW_RECT };
+    let mut ctx: *mut sys::kopek_mgpu = std::ptr::null_mut();
+    let st = unsafe {
+        sys::kopek_mgpu_create(&mut ctx, devices.as_ptr(), devices.len() as u32, n, hop, window, sys::KOPEK_OUT_MAG,
+                               sys::KOPEK_BINS_HALF, 0)
+    };
     if st != sys::KOPEK_OK {
-        panic!("kopek::fft::stft_magnitude: {}", last_error());
+        panic!("kopek::fft::stft_magnitude_multi: {}", last_error());
     }
-    let frames = unsafe { sys::kopek_plan_frames(plan, samples.len() as u64) } as usize;
-    let bins = unsafe { sys::kopek_plan_bins(plan) } as usize;
+    let bins = unsafe { sys::kopek_mgpu_bins(ctx) } as usize;
+    let frames = if samples.len() < n as usize { 0 } else { 1 + (samples.len() - n as usize) / hop as usize };
     let mut flat = vec![0f32; frames * bins];
     let mut got = 0u64;
     let st = unsafe {
-        sys::kopek_stft_exec_host(plan, samples.as_ptr(), samples.len() as u64, flat.as_mut_ptr() as *mut _, &mut got)
+        sys::kopek_mgpu_exec_host(ctx, samples.as_ptr(), samples.len() as u64, flat.as_mut_ptr() as *mut _, &mut got)
     };
-    unsafe { sys::kopek_plan_destroy(plan) };
-    if st != sys::KOPEK_OK {
-        panic!("kopek::fft::stft_magnitude: {}", last_error());
+    let msg = if st != sys::KOPEK_OK { Some(last_error()) } else { None };
+    unsafe { sys::kopek_mgpu_destroy(ctx) };
+    if let Some(m) = msg {
+        panic!("kopek::fft::stft_magnitude_multi: {}", m);
     }
     flat.chunks(bins).map(|r| r.to_vec()).collect()
 }

@@ -47,6 +47,14 @@ def main():
     rng = np.random.default_rng(5)
     z = rng.standard_normal(1000) + 1j * rng.standard_normal(1000)
     np.savez_compressed(os.path.join(HERE, "ragged1000.npz"), input=z, spectrum=np.fft.fft(z, 1024))
+    # inputs of the Rust pinning kit (rust/golden): interleaved (re, im) f64, little endian -- what the reference's
+    # callers hand to fft(): f32 samples widened to f64, im = 0 (examples/beep/view.rs:140-144)
+    for name, arr in (("sine440", oracle.marshal(s)),                                  # configs[0], 1024 points
+                      ("ragged1000", z),                                               # zero-padded to 1024
+                      ("noise256", oracle.marshal(x[:256])),                           # one configs[2] frame
+                      ("len0", np.zeros(0, np.complex128)), ("len1", np.array([2.5 - 1.5j])), ("len3", z[:3]),
+                      ("pcm4096", oracle.marshal(signals.chirp(4096, 48000.0, 20.0, 20000.0), 32767.0))):   # the /32767 quirk
+        np.ascontiguousarray(arr, dtype="<c16").tofile(os.path.join(HERE, f"rust_in_{name}.bin"))
     # show() text
     txt = "label\n1.0000+2.0000i, -0.5000-0.2500i, 0.0000+0.0000i, -0.0000-3.1416i\n"
     with open(os.path.join(HERE, "show.txt"), "w") as f:

@@ -64,3 +64,43 @@ def test_drop_in_device_stays_in_bounds(built_lib):
     _lib.check(_lib.load().kopek_fft_c2c_f64_device(x.data_ptr(), n_in, batch, out.data_ptr(), 0,
                                                     torch.cuda.current_stream().cuda_stream))
     _check(obuf, batch * 1024)
+
+
+def test_exec_host_drains_every_chunk_before_reporting_a_failure(built_lib, monkeypatch):
+    """Fault injection (KOPEK_TEST_FAIL_CHUNK): the enqueue of chunk 2 fails while chunks 0 and 1 are in flight on
+    the other slot streams.  The call must report the failure AND have drained those chunks: their rows are complete
+    in the caller's buffer when it returns (the caller may free it immediately), later rows are untouched, and the
+    plan stays usable."""
+    from kopek_b200 import KopekError, StftPlan, signals
+    n, frames = 1024, 4096
+    x = signals.sine_frames(frames, n)
+    monkeypatch.setenv("KOPEK_HOST_CHUNK_MB", "1")               # 256 frames per chunk -> 16 chunks
+    with StftPlan(n, n, 1, 1) as plan:
+        ref = plan.exec_host(x).copy()
+        out = np.full((frames, plan.pitch), SENT, dtype=np.float32)
+        monkeypatch.setenv("KOPEK_TEST_FAIL_CHUNK", "2")
+        with pytest.raises(KopekError, match="injected"):
+            plan.exec_host_ptr(x.ctypes.data, x.size, out.ctypes.data)
+        assert plan.last_launches == 2
+        assert np.array_equal(out[:512], ref[:512]), "chunks enqueued before the failure were not drained"
+        assert (out[512:] == SENT).all()
+        monkeypatch.delenv("KOPEK_TEST_FAIL_CHUNK")
+        assert np.array_equal(plan.exec_host(x), ref)
+
+
+def test_exec_host_chunks_are_sized_by_the_busier_direction(built_lib):
+    """hop = 1 writes 2049 x 4 bytes per 4 bytes read; slots must be sized by the output, not the input
+    (the first version asked for ~34 GB per slot here)."""
+    import torch
+    from kopek_b200 import StftPlan, signals
+    n, hop = 4096, 1
+    x = signals.white_noise(n + 20000, seed=3)
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    with StftPlan(n, hop, 1, 1) as plan:
+        got = plan.exec_host(x)
+        used = free0 - torch.cuda.mem_get_info()[0]
+        assert used < (1 << 30), f"chunk slots took {used >> 20} MiB"
+        with StftPlan(n, 1024, 1, 1) as coarse:
+            ref = coarse.exec_host(x)
+        assert np.array_equal(got[::1024], ref)

@@ -44,3 +44,19 @@ def test_live_spectrum_complex_and_errors(built_lib, oracle_mod):
         LiveSpectrum(1000)                       # not a supported frame size
     with pytest.raises(KopekError):
         LiveSpectrum(1024, window=3)             # custom windows are not a stream option
+
+
+def test_live_bands_with_unaligned_push_sizes(built_lib, oracle_mod):
+    """441-sample pushes (one UI frame of 44.1 kHz audio at 100 Hz) make the cumulative count odd; the
+    window handed to the kernel stays aligned, so the band epilogue keeps working and every push runs the same kernel."""
+    from kopek_b200 import LiveSpectrum, OUT_BANDS_LOG, OUT_MAG
+    rng = np.random.default_rng(9)
+    bands, mags = LiveSpectrum(1024, 0, OUT_BANDS_LOG), LiveSpectrum(1024, 0, OUT_MAG)
+    for count in (441, 441, 1, 441, 3, 1024, 441):
+        new = rng.standard_normal(count).astype(np.float32)
+        row, y = bands.push(new), mags.push(new)
+        want = oracle_mod.bands_log(y.astype(np.float32)[:512])
+        assert row.shape == (10,)
+        assert np.abs(row[:8] - want).max() <= 1e-4 * want.max()
+    bands.close()
+    mags.close()
