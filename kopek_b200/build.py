@@ -83,8 +83,6 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False, 
     extra = list(defs)
     if os.environ.get("KOPEK_K1_PREF") is not None:   # tuning: force the K1 register prefetch on/off for every size
         extra.append("-DK1_PREF_ALL=" + ("true" if os.environ["KOPEK_K1_PREF"] == "1" else "false"))
-    if os.environ.get("KOPEK_K1W_SWEEP"):      # build every K1W tuning variant (tools/sweep_k1w.py)
-        extra.append("-DKOPEK_K1W_SWEEP")
     stamp = _fingerprint(extra)
     if not force and not ptxas_info and not _stale(LIB, stamp):
         return LIB
@@ -97,7 +95,11 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False, 
         obj = os.path.join(OBJ, f"k1_{n}.o")
         jobs.append((obj, [cc, *ARCH, *COMMON, *extra, f"-DKOPEK_K1_N={n}", "-c", os.path.join(CSRC, "k1_inst.cu"),
                            "-o", obj]))
-    for name in ("kopek_cuda", "k1w_inst", "k1m_inst", "fft_large", "synth", "pcm", "dist_fft", "mgpu"):
+    for r in (4, 8):
+        obj = os.path.join(OBJ, f"k1m_{r}.o")
+        jobs.append((obj, [cc, *ARCH, *COMMON, *extra, f"-DKOPEK_K1M_R={r}", "-c", os.path.join(CSRC, "k1m_inst.cu"),
+                           "-o", obj]))
+    for name in ("kopek_cuda", "k1w_inst", "fft_large", "synth", "pcm", "dist_fft", "mgpu"):
         src = os.path.join(CSRC, name + ".cu")
         if os.path.exists(src):
             obj = os.path.join(OBJ, name + ".o")

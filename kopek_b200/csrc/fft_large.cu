@@ -29,7 +29,7 @@
 // profiles/r1_f32x2_sweep.txt), so they keep the scalar form.
 #define KOPEK_F32X2
 #include "fft_batched.cuh"
-#include "fft_warp1024.cuh"
+#include "lane_common.cuh"
 
 namespace kopek {
 

@@ -119,7 +119,9 @@ __device__ __forceinline__ float cs16_sin(int n1) { return cs16_cos((n1 + 12) & 
 // 128-lane teams (or six 64-lane teams) stay resident per SM.  The sum has an absolute error of ~3e-8, which is a
 // large RELATIVE error where the window itself is ~1e-7 (the first and last samples of a frame), so the two edge
 // sixteenths (n1 = 0 and n1 = 15) keep their table values; everywhere else w/2 >= 0.019 and the error is < 2e-6.
-template <int R, int OUT, int WINK, int MINB, int PF>
+// FULL: all N bins per row (the conjugate mirror X[N - k] stored beside the computed half, see fft_warp1024b.cuh);
+// VEC == false: frames start at any 4-byte aligned sample (odd hop / unaligned base): two 32-bit loads per pair.
+template <int R, int OUT, int WINK, int MINB, int PF, bool FULL = false, bool VEC = true>
 __global__ void __launch_bounds__(16 * R, MINB)
 k1m_kernel(const K1WParams p) {
     constexpr bool WIN = WINK != 0;
@@ -162,9 +164,15 @@ k1m_kernel(const K1WParams p) {
     const float sgn = (r & 1) ? -1.0f : 1.0f;               // W_R^{r R/2}
 
     auto load_frame = [&](uint64_t fr, float2 *dst) {
-        const float2 *xf = reinterpret_cast<const float2 *>(p.x + fr * p.hop) + t;
+        if constexpr (VEC) {
+            const float2 *xf = reinterpret_cast<const float2 *>(p.x + fr * p.hop) + t;
 #pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) dst[n1] = ldg_stream2(xf + T * n1);
+            for (int n1 = 0; n1 < 16; ++n1) dst[n1] = ldg_stream2(xf + T * n1);
+        } else {
+            const float *xs = p.x + fr * p.hop + 2 * t;
+#pragma unroll
+            for (int n1 = 0; n1 < 16; ++n1) dst[n1] = make_float2(__ldg(xs + 2 * T * n1), __ldg(xs + 2 * T * n1 + 1));
+        }
     };
     float2 vn[16];
     if (blockIdx.x < p.n_frames) load_frame(blockIdx.x, vn);
@@ -277,18 +285,30 @@ k1m_kernel(const K1WParams p) {
         constexpr int EB = OUT == OUT_COMPLEX ? 8 : 4;
         char *o_lo = reinterpret_cast<char *>(p.out) + (frame * p.pitch + t) * EB;
         char *o_hi = reinterpret_cast<char *>(p.out) + (frame * p.pitch + (M - t)) * EB;
+        // mirrors (FULL): bin k also lands at N - k; k = 0 and k = M (lane 0, i = 0) have none
+        char *m_lo = reinterpret_cast<char *>(p.out) + (frame * p.pitch + (2 * M - t)) * EB;
+        char *m_hi = reinterpret_cast<char *>(p.out) + (frame * p.pitch + (M + t)) * EB;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const float2 A = a[i], B = b[i];
             float2 Sx = make_float2(A.x + B.x, A.y - B.y);
             float2 Dx = make_float2(A.x - B.x, A.y + B.y);
             float2 Qx = cmul(mul_w32(Dx, i), pw_lane);       // -i W_N^{t + T i} = (-i W_N^t) W32^i
-            emit_at<OUT, WIN>(o_lo + T * i * EB, Sx + Qx);
-            emit_at<OUT, WIN>(o_hi - T * i * EB, make_float2(Sx.x - Qx.x, Qx.y - Sx.y));
+            if constexpr (FULL) {
+                const bool edge = i == 0 && t == 0;
+                emit_pair<OUT, WIN>(o_lo + T * i * EB, edge ? nullptr : m_lo - T * i * EB, Sx + Qx);
+                emit_pair<OUT, WIN>(o_hi - T * i * EB, edge ? nullptr : m_hi + T * i * EB,
+                                    make_float2(Sx.x - Qx.x, Qx.y - Sx.y));
+            } else {
+                emit_at<OUT, WIN>(o_lo + T * i * EB, Sx + Qx);
+                emit_at<OUT, WIN>(o_hi - T * i * EB, make_float2(Sx.x - Qx.x, Qx.y - Sx.y));
+            }
         }
         if (t == 0) {                                        // bin N/4 = conj Z[M/2]
             const float2 zm = zs[T / 2];
-            emit_at<OUT, WIN>(o_lo + (M / 2) * EB, make_float2(2.0f * zm.x, -2.0f * zm.y));
+            const float2 Xq = make_float2(2.0f * zm.x, -2.0f * zm.y);
+            if constexpr (FULL) emit_pair<OUT, WIN>(o_lo + (M / 2) * EB, m_lo - (M / 2) * EB, Xq);
+            else emit_at<OUT, WIN>(o_lo + (M / 2) * EB, Xq);
         }
     }
 }

@@ -52,11 +52,17 @@ __device__ __forceinline__ float pcm16_sample(float raw_bits, uint32_t shift) {
     return fmaf(fmaf(-q, 32767.0f, sf), r, q);
 }
 
-template <int OUT, bool WIN, int WARPS, int MINB, bool BULK = false, bool PCM = false>
+// FULL: all n = 1024 bins per row, as the reference's callers iterate them (examples/graph/utils.rs:47-63): bins
+// 513..1023 are the conjugate mirror X[n - k] = conj X[k] of a real frame, so every value is computed once and stored
+// twice (the mirror of a 64-byte run of bins is a 64-byte run again).
+// VEC == false: frames start at any 4-byte aligned sample (odd hop, unaligned base): the 64-bit pair loads become two
+// 32-bit loads each -- the same bytes over the same wavefronts, sixteen more load instructions per frame.
+template <int OUT, bool WIN, int WARPS, int MINB, bool BULK = false, bool PCM = false, bool FULL = false, bool VEC = true>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 k1w_1024b_kernel(const K1WParams p) {
     constexpr int M = 512;
     static_assert(!BULK || (OUT == OUT_MAG || OUT == OUT_POWER || OUT == OUT_DB), "bulk store: f32 spectra only");
+    static_assert(!FULL || (!BULK && OUT <= OUT_DB), "full rows: spectra written directly");
     constexpr int WARP_F2 = K1B_EX_F2 + (BULK ? K1B_STAGE_F2 : 0);
     extern __shared__ __align__(16) unsigned char k1b_smem[];
     const int l = threadIdx.x & 31, k1 = l >> 1, par = l & 1;
@@ -85,9 +91,15 @@ k1w_1024b_kernel(const K1WParams p) {
     const uint64_t total_warps = (uint64_t)gridDim.x * WARPS;
     const uint64_t first = (uint64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
     auto load_frame = [&](uint64_t fr, float2 *dst) {
-        const float2 *xf = reinterpret_cast<const float2 *>(p.x + fr * p.hop) + l;
+        if constexpr (PCM || VEC) {
+            const float2 *xf = reinterpret_cast<const float2 *>(p.x + fr * p.hop) + l;
 #pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) dst[n1] = __ldg(xf + 32 * n1);
+            for (int n1 = 0; n1 < 16; ++n1) dst[n1] = __ldg(xf + 32 * n1);
+        } else {
+            const float *xs = p.x + fr * p.hop + 2 * l;
+#pragma unroll
+            for (int n1 = 0; n1 < 16; ++n1) dst[n1] = make_float2(__ldg(xs + 64 * n1), __ldg(xs + 64 * n1 + 1));
+        }
     };
     float2 vn[16];
     if (first < p.n_frames) load_frame(first, vn);
@@ -227,16 +239,31 @@ k1w_1024b_kernel(const K1WParams p) {
                 o_lo = reinterpret_cast<char *>(stage + (k1 + 128 * par));
                 o_hi = reinterpret_cast<char *>(stage + (M - k1 - 128 * par));
             }
+            // mirrors (FULL): bin k also lands at n - k; k = 0 (lane 0, i = 0, lower store) and k = 512 (its upper
+            // store) have none
+            char *m_lo = reinterpret_cast<char *>(p.out) + (frame * p.pitch + (2 * M - k1 - 128 * par)) * EB;
+            char *m_hi = reinterpret_cast<char *>(p.out) + (frame * p.pitch + (M + k1 + 128 * par)) * EB;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float2 A = zl[i], B = b[i];
                 float2 S = make_float2(A.x + B.x, A.y - B.y);
                 float2 D = make_float2(A.x - B.x, A.y + B.y);
                 float2 Q = cmul(mul_w64(D, i), pw_lane);        // -i W1024^{k1 + 128 par + 16 i}
-                emit_at<OUT, WIN>(o_lo + 16 * i * EB, S + Q);
-                emit_at<OUT, WIN>(o_hi - 16 * i * EB, make_float2(S.x - Q.x, Q.y - S.y));
+                if constexpr (FULL) {
+                    const bool edge = i == 0 && l == 0;         // bins 0 and 512: no mirror
+                    emit_pair<OUT, WIN>(o_lo + 16 * i * EB, edge ? nullptr : m_lo - 16 * i * EB, S + Q);
+                    emit_pair<OUT, WIN>(o_hi - 16 * i * EB, edge ? nullptr : m_hi + 16 * i * EB,
+                                        make_float2(S.x - Q.x, Q.y - S.y));
+                } else {
+                    emit_at<OUT, WIN>(o_lo + 16 * i * EB, S + Q);
+                    emit_at<OUT, WIN>(o_hi - 16 * i * EB, make_float2(S.x - Q.x, Q.y - S.y));
+                }
             }
-            if (l == 0) emit_at<OUT, WIN>(o_lo + (M / 2) * EB, make_float2(2.0f * zu[0].x, -2.0f * zu[0].y));   // bin 256
+            if (l == 0) {                                                                                      // bin 256
+                const float2 X256 = make_float2(2.0f * zu[0].x, -2.0f * zu[0].y);
+                if constexpr (FULL) emit_pair<OUT, WIN>(o_lo + (M / 2) * EB, m_lo - (M / 2) * EB, X256);
+                else emit_at<OUT, WIN>(o_lo + (M / 2) * EB, X256);
+            }
             if constexpr (BULK) {
                 __syncwarp();
                 if (l == 0) {

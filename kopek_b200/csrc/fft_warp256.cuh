@@ -15,7 +15,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "fft_warp1024.cuh"
+#include "lane_common.cuh"
 
 namespace kopek {
 
@@ -36,7 +36,9 @@ __device__ __forceinline__ float2 mul_w32(float2 v, int k0) {
     return k0 == 0 ? v : cmul_const(v, c[k0], s[k0]);
 }
 
-template <int OUT, bool WIN, int WARPS, int MINB>
+// FULL / VEC: see fft_warp1024b.cuh (all N bins per row with the conjugate mirror stored beside the computed half;
+// VEC == false reads frames that start at any 4-byte aligned sample with four 32-bit loads per quad).
+template <int OUT, bool WIN, int WARPS, int MINB, bool FULL = false, bool VEC = true>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 k1w_256_kernel(const K1WParams p) {
     constexpr int M = 128;
@@ -70,9 +72,17 @@ k1w_256_kernel(const K1WParams p) {
     auto load_group = [&](uint64_t grp, float4 *dst) {
         uint64_t fr = 4 * grp + g;
         if (fr >= p.n_frames) fr = p.n_frames - 1;
-        const float4 *xf = reinterpret_cast<const float4 *>(p.x + fr * p.hop) + a;
+        if constexpr (VEC) {
+            const float4 *xf = reinterpret_cast<const float4 *>(p.x + fr * p.hop) + a;
 #pragma unroll
-        for (int n1 = 0; n1 < 8; ++n1) dst[n1] = ldg_stream(xf + 8 * n1);
+            for (int n1 = 0; n1 < 8; ++n1) dst[n1] = ldg_stream(xf + 8 * n1);
+        } else {
+            const float *xs = p.x + fr * p.hop + 4 * a;
+#pragma unroll
+            for (int n1 = 0; n1 < 8; ++n1)
+                dst[n1] = make_float4(__ldg(xs + 32 * n1), __ldg(xs + 32 * n1 + 1), __ldg(xs + 32 * n1 + 2),
+                                      __ldg(xs + 32 * n1 + 3));
+        }
     };
     float4 vn[8];
     if (first < n_groups) load_group(first, vn);
@@ -138,6 +148,8 @@ k1w_256_kernel(const K1WParams p) {
         constexpr int EB = OUT == OUT_COMPLEX ? 8 : 4;
         char *o_lo = reinterpret_cast<char *>(p.out) + (frame * p.pitch + a) * EB;
         char *o_hi = reinterpret_cast<char *>(p.out) + (frame * p.pitch + (M - a)) * EB;
+        char *m_lo = reinterpret_cast<char *>(p.out) + (frame * p.pitch + (2 * M - a)) * EB;   // mirrors (FULL): bin N - k
+        char *m_hi = reinterpret_cast<char *>(p.out) + (frame * p.pitch + (M + a)) * EB;
         if (valid) {
 #pragma unroll
             for (int k0 = 0; k0 < 8; ++k0) {
@@ -145,10 +157,21 @@ k1w_256_kernel(const K1WParams p) {
                 float2 S = make_float2(A.x + B.x, A.y - B.y);
                 float2 D = make_float2(A.x - B.x, A.y + B.y);
                 float2 Q = cmul(mul_w32(D, k0), pw_lane);
-                emit_at<OUT, WIN>(o_lo + 8 * k0 * EB, S + Q);
-                emit_at<OUT, WIN>(o_hi - 8 * k0 * EB, make_float2(S.x - Q.x, Q.y - S.y));
+                if constexpr (FULL) {
+                    const bool edge = k0 == 0 && a == 0;      // bins 0 and M: no mirror
+                    emit_pair<OUT, WIN>(o_lo + 8 * k0 * EB, edge ? nullptr : m_lo - 8 * k0 * EB, S + Q);
+                    emit_pair<OUT, WIN>(o_hi - 8 * k0 * EB, edge ? nullptr : m_hi + 8 * k0 * EB,
+                                        make_float2(S.x - Q.x, Q.y - S.y));
+                } else {
+                    emit_at<OUT, WIN>(o_lo + 8 * k0 * EB, S + Q);
+                    emit_at<OUT, WIN>(o_hi - 8 * k0 * EB, make_float2(S.x - Q.x, Q.y - S.y));
+                }
             }
-            if (a == 0) emit_at<OUT, WIN>(o_lo + (M / 2) * EB, make_float2(2.0f * e[8].x, -2.0f * e[8].y));
+            if (a == 0) {
+                const float2 Xq = make_float2(2.0f * e[8].x, -2.0f * e[8].y);
+                if constexpr (FULL) emit_pair<OUT, WIN>(o_lo + (M / 2) * EB, m_lo - (M / 2) * EB, Xq);
+                else emit_at<OUT, WIN>(o_lo + (M / 2) * EB, Xq);
+            }
         }
         __syncwarp();
     }

@@ -25,7 +25,9 @@ constexpr int K512_TABLE_F2 = K512_WIN_F2 + K512_TW_F2 + K512_PW_F2;
 constexpr int K512_FRAME_F2 = 16 * 17;     // exchange positions per frame
 constexpr int K512_EX_F2 = 2 * K512_FRAME_F2;
 
-template <int OUT, bool WIN, int WARPS, int MINB>
+// FULL / VEC: see fft_warp1024b.cuh (all N bins per row with the conjugate mirror stored beside the computed half;
+// VEC == false reads frames that start at any 4-byte aligned sample with two 32-bit loads per pair).
+template <int OUT, bool WIN, int WARPS, int MINB, bool FULL = false, bool VEC = true>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 k1w_512_kernel(const K1WParams p) {
     constexpr int M = 256;
@@ -54,9 +56,15 @@ k1w_512_kernel(const K1WParams p) {
     auto load_group = [&](uint64_t grp, float2 *dst) {
         uint64_t fr = 2 * grp + g;
         if (fr >= p.n_frames) fr = p.n_frames - 1;
-        const float2 *xf = reinterpret_cast<const float2 *>(p.x + fr * p.hop) + a;
+        if constexpr (VEC) {
+            const float2 *xf = reinterpret_cast<const float2 *>(p.x + fr * p.hop) + a;
 #pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) dst[n1] = __ldg(xf + 16 * n1);
+            for (int n1 = 0; n1 < 16; ++n1) dst[n1] = __ldg(xf + 16 * n1);
+        } else {
+            const float *xs = p.x + fr * p.hop + 2 * a;
+#pragma unroll
+            for (int n1 = 0; n1 < 16; ++n1) dst[n1] = make_float2(__ldg(xs + 32 * n1), __ldg(xs + 32 * n1 + 1));
+        }
     };
     float2 vn[16];
     if (first < n_groups) load_group(first, vn);
@@ -94,6 +102,8 @@ k1w_512_kernel(const K1WParams p) {
         constexpr int EB = OUT == OUT_COMPLEX ? 8 : 4;
         char *o_lo = reinterpret_cast<char *>(p.out) + (frame * p.pitch + a) * EB;
         char *o_hi = reinterpret_cast<char *>(p.out) + (frame * p.pitch + (M - a)) * EB;
+        char *m_lo = reinterpret_cast<char *>(p.out) + (frame * p.pitch + (2 * M - a)) * EB;   // mirrors (FULL): bin N - k
+        char *m_hi = reinterpret_cast<char *>(p.out) + (frame * p.pitch + (M + a)) * EB;
         if (valid) {
 #pragma unroll
             for (int k0 = 0; k0 < 8; ++k0) {
@@ -101,10 +111,21 @@ k1w_512_kernel(const K1WParams p) {
                 float2 S = make_float2(A.x + B.x, A.y - B.y);
                 float2 D = make_float2(A.x - B.x, A.y + B.y);
                 float2 Q = cmul(mul_w32(D, k0), pw_lane);     // -i W512^{a + 16 k0} = (-i W512^a) W32^{k0}
-                emit_at<OUT, WIN>(o_lo + 16 * k0 * EB, S + Q);
-                emit_at<OUT, WIN>(o_hi - 16 * k0 * EB, make_float2(S.x - Q.x, Q.y - S.y));
+                if constexpr (FULL) {
+                    const bool edge = k0 == 0 && a == 0;      // bins 0 and M: no mirror
+                    emit_pair<OUT, WIN>(o_lo + 16 * k0 * EB, edge ? nullptr : m_lo - 16 * k0 * EB, S + Q);
+                    emit_pair<OUT, WIN>(o_hi - 16 * k0 * EB, edge ? nullptr : m_hi + 16 * k0 * EB,
+                                        make_float2(S.x - Q.x, Q.y - S.y));
+                } else {
+                    emit_at<OUT, WIN>(o_lo + 16 * k0 * EB, S + Q);
+                    emit_at<OUT, WIN>(o_hi - 16 * k0 * EB, make_float2(S.x - Q.x, Q.y - S.y));
+                }
             }
-            if (a == 0) emit_at<OUT, WIN>(o_lo + (M / 2) * EB, make_float2(2.0f * e[8].x, -2.0f * e[8].y));
+            if (a == 0) {
+                const float2 Xq = make_float2(2.0f * e[8].x, -2.0f * e[8].y);
+                if constexpr (FULL) emit_pair<OUT, WIN>(o_lo + (M / 2) * EB, m_lo - (M / 2) * EB, Xq);
+                else emit_at<OUT, WIN>(o_lo + (M / 2) * EB, Xq);
+            }
         }
         __syncwarp();
     }

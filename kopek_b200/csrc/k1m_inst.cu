@@ -1,12 +1,22 @@
-// K1M instantiations (fft_team.cuh): team-per-frame kernels for N = 2048 (R = 4) and 4096 (R = 8); R = 2 (N = 1024)
-// is built for testing only (KOPEK_K1W_VARIANT=300).
+// K1M instantiations (fft_team.cuh): team-per-frame kernels for N = 2048 (R = 4) and 4096 (R = 8).  Compiled once per
+// R (-DKOPEK_K1M_R=4 / 8, kopek_b200/build.py) so that the two sets of instantiations build in parallel; the host
+// tables and the dispatcher live in the R = 4 object.
 #include <cmath>
 
+// Complex add / subtract as ONE packed instruction (add/sub.rn.f32x2 -> SASS FADD2) in this translation unit: the team
+// kernels are bound by instruction issue, not by HBM, and 10 % fewer issue slots are worth +2.5 to +4 points of the HBM
+// roofline at both sizes, burst and sustained (profiles/r2_sustained_sweep.txt).  Bit-identical results.
+#define KOPEK_F32X2
 #include "k1w_launch.cuh"
 #include "fft_team.cuh"
 
+#ifndef KOPEK_K1M_R
+#error "compile with -DKOPEK_K1M_R=4 or 8"
+#endif
+
 namespace kopek {
 
+#if KOPEK_K1M_R == 4
 template <int R> static void build_tables_r(const float *half_window, double cs_a, double cs_b, float2 *out) {
     using G = K1MGeom<R>;
     constexpr int T = G::T, QD = G::QD;
@@ -55,7 +65,6 @@ template <int R> static void build_tables_r(const float *half_window, double cs_
 
 int k1m_table_f4(int n) {
     switch (n) {
-        case 1024: return K1MGeom<2>::TABLE_F2 / 2;
         case 2048: return K1MGeom<4>::TABLE_F2 / 2;
         case 4096: return K1MGeom<8>::TABLE_F2 / 2;
         default: return 0;
@@ -64,10 +73,10 @@ int k1m_table_f4(int n) {
 
 void k1m_build_tables(int n, const float *half_window, double cs_a, double cs_b, float4 *out) {
     float2 *o = reinterpret_cast<float2 *>(out);
-    if (n == 1024) build_tables_r<2>(half_window, cs_a, cs_b, o);
-    else if (n == 2048) build_tables_r<4>(half_window, cs_a, cs_b, o);
+    if (n == 2048) build_tables_r<4>(half_window, cs_a, cs_b, o);
     else build_tables_r<8>(half_window, cs_a, cs_b, o);
 }
+#endif
 
 #ifndef KOPEK_K1M_PF
 #define KOPEK_K1M_PF 0      // L2 prefetch distance in frames per team: measured 0/2/3/5 -> no gain (not latency bound on HBM)
@@ -83,9 +92,9 @@ template <int R, int WINK> struct K1MOcc {
     static constexpr int MINB = WINK == 1 ? 8 * 2 / R : KOPEK_K1M_WARPS * 2 / R;
 };
 
-template <int R, int OUT, int WIN>
+template <int R, int OUT, int WIN, bool FULL, bool VEC>
 static cudaError_t launch_m(const K1WParams &p, int grid, cudaStream_t stream, int *occ_out) {
-    auto kern = k1m_kernel<R, OUT, WIN, K1MOcc<R, WIN>::MINB, KOPEK_K1M_PF>;
+    auto kern = k1m_kernel<R, OUT, WIN, K1MOcc<R, WIN>::MINB, KOPEK_K1M_PF, FULL, VEC>;
     constexpr size_t smem = K1MGeom<R>::SMEM;
     if (occ_out) {
         int nb = 0;
@@ -97,33 +106,55 @@ static cudaError_t launch_m(const K1WParams &p, int grid, cudaStream_t stream, i
     return cudaGetLastError();
 }
 
+// mode: 0 = HALF rows, 64-bit loads (every window kind); 1 = FULL rows; 2 = HALF rows, 32-bit loads; 3 = FULL rows,
+// 32-bit loads.  Modes 1..3 exist for the rectangular and cosine-sum windows (wink 0, 2); a custom window table with
+// FULL rows or unaligned frames runs on the generic kernel (kopek_cuda.cu).
+template <int R, int OUT, int WIN>
+static cudaError_t launch_w(const K1WParams &p, int mode, int grid, cudaStream_t stream, int *occ_out) {
+    if constexpr (WIN != 1) {
+        if (mode == 1) return launch_m<R, OUT, WIN, true, true>(p, grid, stream, occ_out);
+        if (mode == 2) return launch_m<R, OUT, WIN, false, false>(p, grid, stream, occ_out);
+        if (mode == 3) return launch_m<R, OUT, WIN, true, false>(p, grid, stream, occ_out);
+    }
+    if (mode != 0) return cudaErrorInvalidValue;
+    return launch_m<R, OUT, WIN, false, true>(p, grid, stream, occ_out);
+}
+
 template <int R>
-static cudaError_t launch_r(const K1WParams &p, int output, int wink, int grid, cudaStream_t stream, int *occ_out) {
+static cudaError_t launch_r(const K1WParams &p, int output, int wink, int mode, int grid, cudaStream_t stream,
+                            int *occ_out) {
     switch (output * 3 + wink) {
-        case 0: return launch_m<R, OUT_COMPLEX, 0>(p, grid, stream, occ_out);
-        case 1: return launch_m<R, OUT_COMPLEX, 1>(p, grid, stream, occ_out);
-        case 2: return launch_m<R, OUT_COMPLEX, 2>(p, grid, stream, occ_out);
-        case 3: return launch_m<R, OUT_MAG, 0>(p, grid, stream, occ_out);
-        case 4: return launch_m<R, OUT_MAG, 1>(p, grid, stream, occ_out);
-        case 5: return launch_m<R, OUT_MAG, 2>(p, grid, stream, occ_out);
-        case 6: return launch_m<R, OUT_POWER, 0>(p, grid, stream, occ_out);
-        case 7: return launch_m<R, OUT_POWER, 1>(p, grid, stream, occ_out);
-        case 8: return launch_m<R, OUT_POWER, 2>(p, grid, stream, occ_out);
-        case 9: return launch_m<R, OUT_DB, 0>(p, grid, stream, occ_out);
-        case 10: return launch_m<R, OUT_DB, 1>(p, grid, stream, occ_out);
-        case 11: return launch_m<R, OUT_DB, 2>(p, grid, stream, occ_out);
+        case 0: return launch_w<R, OUT_COMPLEX, 0>(p, mode, grid, stream, occ_out);
+        case 1: return launch_w<R, OUT_COMPLEX, 1>(p, mode, grid, stream, occ_out);
+        case 2: return launch_w<R, OUT_COMPLEX, 2>(p, mode, grid, stream, occ_out);
+        case 3: return launch_w<R, OUT_MAG, 0>(p, mode, grid, stream, occ_out);
+        case 4: return launch_w<R, OUT_MAG, 1>(p, mode, grid, stream, occ_out);
+        case 5: return launch_w<R, OUT_MAG, 2>(p, mode, grid, stream, occ_out);
+        case 6: return launch_w<R, OUT_POWER, 0>(p, mode, grid, stream, occ_out);
+        case 7: return launch_w<R, OUT_POWER, 1>(p, mode, grid, stream, occ_out);
+        case 8: return launch_w<R, OUT_POWER, 2>(p, mode, grid, stream, occ_out);
+        case 9: return launch_w<R, OUT_DB, 0>(p, mode, grid, stream, occ_out);
+        case 10: return launch_w<R, OUT_DB, 1>(p, mode, grid, stream, occ_out);
+        case 11: return launch_w<R, OUT_DB, 2>(p, mode, grid, stream, occ_out);
         default: return cudaErrorInvalidValue;
     }
 }
 
-cudaError_t k1m_launch(int n, const K1WParams &p, int output, int wink, int grid, cudaStream_t stream, int *occ_out) {
-    if (wink < 0 || wink > 2) return cudaErrorInvalidValue;
+#if KOPEK_K1M_R == 4
+cudaError_t k1m_launch_r8(const K1WParams &p, int output, int wink, int mode, int grid, cudaStream_t stream, int *occ_out);
+cudaError_t k1m_launch(int n, const K1WParams &p, int output, int wink, int mode, int grid, cudaStream_t stream,
+                       int *occ_out) {
+    if (wink < 0 || wink > 2 || mode < 0 || mode > 3) return cudaErrorInvalidValue;
     switch (n) {
-        case 1024: return launch_r<2>(p, output, wink, grid, stream, occ_out);
-        case 2048: return launch_r<4>(p, output, wink, grid, stream, occ_out);
-        case 4096: return launch_r<8>(p, output, wink, grid, stream, occ_out);
+        case 2048: return launch_r<4>(p, output, wink, mode, grid, stream, occ_out);
+        case 4096: return k1m_launch_r8(p, output, wink, mode, grid, stream, occ_out);
         default: return cudaErrorInvalidValue;
     }
 }
+#else
+cudaError_t k1m_launch_r8(const K1WParams &p, int output, int wink, int mode, int grid, cudaStream_t stream, int *occ_out) {
+    return launch_r<8>(p, output, wink, mode, grid, stream, occ_out);
+}
+#endif
 
 }  // namespace kopek

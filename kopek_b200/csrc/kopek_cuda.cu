@@ -291,7 +291,7 @@ struct kopek_plan {
     float4 *d_k1w;     // tables of the sub-warp kernels (n == 256 / 512); n == 1024: the three-pass kernel in tuning builds
     float4 *d_k1b;     // tables of the two-exchange 1024-point kernel
     int k1b_warps_per_sm;
-    float4 *d_k1m;     // tables of the team-per-frame kernel (n == 2048 / 4096; n == 1024 with KOPEK_K1W_VARIANT=300)
+    float4 *d_k1m;     // tables of the team-per-frame kernel (n == 2048 / 4096)
     int k1m_teams_per_sm, k1m_wink;
     int k1w_variant, k1w_warps_per_sm;
     float band_scale;
@@ -331,13 +331,6 @@ static kopek_status upload_window(kopek_plan *p, const float *w) {
         k1b_build_tables(half.data(), tb.data());
         KOPEK_CUDA(cudaMemcpy(p->d_k1b, tb.data(), sizeof(float4) * K1B_TABLE_F4, cudaMemcpyHostToDevice));
     }
-#ifdef KOPEK_K1W_SWEEP
-    if (p->d_k1w && p->n == 1024) {
-        std::vector<float4> t(K1W_TABLE_F4);
-        k1w_build_tables(half.data(), t.data());
-        KOPEK_CUDA(cudaMemcpy(p->d_k1w, t.data(), sizeof(float4) * K1W_TABLE_F4, cudaMemcpyHostToDevice));
-    }
-#endif
     if (p->d_k1w && p->n == 256) {
         std::vector<float4> t(K1W256_TABLE_F4);
         k1w256_build_tables(half.data(), t.data());
@@ -481,7 +474,6 @@ kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint
     if (bands && (n != 1024 || bins != KOPEK_BINS_HALF))
         return fail(KOPEK_ERR_UNSUPPORTED, "band epilogues need n = 1024 and KOPEK_BINS_HALF (the reference's callers "
                                            "analyse 1024-sample frames)");
-    if (bands && hop % 4 != 0) return fail(KOPEK_ERR_UNSUPPORTED, "band epilogues need hop %% 4 == 0");
     if (bins > KOPEK_BINS_FULL) return fail(KOPEK_ERR_INVALID, "unknown bins mode %u", bins);
     const uint64_t nb = bands ? KOPEK_BAND_ROW : bins == KOPEK_BINS_FULL ? n : n / 2 + 1;
     if (out_pitch_elems == 0) out_pitch_elems = nb;
@@ -540,30 +532,12 @@ kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint
         }
         if (n == 1024) {
             // headline size: the two-exchange warp-per-frame kernel (fft_warp1024b.cuh), every output; K1 stays for
-            // FULL bins / odd hops.  KOPEK_K1W_VARIANT (tuning): < 0 generic K1, 300 team kernel with R = 2,
-            // 0..13 the three-pass kernel of fft_warp1024.cuh (only in -DKOPEK_K1W_SWEEP builds).
+            // the generic K1 is kept as a cross-check (KOPEK_K1W_VARIANT < 0)
             const char *env = getenv("KOPEK_K1W_VARIANT");
             p->k1w_variant = env ? atoi(env) : 200;
-#ifndef KOPEK_K1W_SWEEP
             if (p->k1w_variant >= 0) p->k1w_variant = std::max(p->k1w_variant, 200);
-#endif
             if (p->k1w_variant < 0 && bands) p->k1w_variant = 200;      // the generic kernel has no band epilogue
             K1WParams dummy{};
-#ifdef KOPEK_K1W_SWEEP
-            if (p->k1w_variant >= 0 && p->k1w_variant < 200) {
-                std::vector<float4> t(K1W_TABLE_F4);
-                k1w_build_tables(nullptr, t.data());
-                if ((e = cudaMalloc(&p->d_k1w, sizeof(float4) * K1W_TABLE_F4)) != cudaSuccess ||
-                    (e = cudaMemcpy(p->d_k1w, t.data(), sizeof(float4) * K1W_TABLE_F4, cudaMemcpyHostToDevice)) !=
-                        cudaSuccess ||
-                    (e = k1w_launch(dummy, (int)output, window != KOPEK_WINDOW_RECT, p->k1w_variant, 0, nullptr,
-                                    &p->k1w_warps_per_sm)) != cudaSuccess ||
-                    p->k1w_warps_per_sm <= 0) {
-                    st = fail(KOPEK_ERR_CUDA, "K1W setup failed: %s", cudaGetErrorString(e));
-                    break;
-                }
-            }
-#endif
             if (p->k1w_variant >= 200) {
                 std::vector<float4> tb(K1B_TABLE_F4);
                 k1b_build_tables(nullptr, tb.data());
@@ -592,8 +566,8 @@ kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint
                     break;
                 }
                 K1WParams dummy{};
-                e = n == 256 ? k1w256_launch(dummy, (int)output, window != KOPEK_WINDOW_RECT, 0, nullptr, &p->k1w_warps_per_sm)
-                             : k1w512_launch(dummy, (int)output, window != KOPEK_WINDOW_RECT, 0, nullptr, &p->k1w_warps_per_sm);
+                e = n == 256 ? k1w256_launch(dummy, (int)output, window != KOPEK_WINDOW_RECT, 0, 0, nullptr, &p->k1w_warps_per_sm)
+                             : k1w512_launch(dummy, (int)output, window != KOPEK_WINDOW_RECT, 0, 0, nullptr, &p->k1w_warps_per_sm);
                 if (e != cudaSuccess || p->k1w_warps_per_sm <= 0) {
                     st = fail(KOPEK_ERR_CUDA, "K1W-%u kernel cannot be resident: %s", n, cudaGetErrorString(e));
                     break;
@@ -604,7 +578,7 @@ kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint
             // team-per-frame kernel (fft_team.cuh): 2048 / 4096 points; K1 stays for FULL bins / odd hops
             const char *env = getenv("KOPEK_K1W_VARIANT");
             const int v = env ? atoi(env) : 0;
-            if (output <= KOPEK_OUT_DB && ((v >= 0 && (n == 2048 || n == 4096)) || (v == 300 && n == 1024))) {
+            if (output <= KOPEK_OUT_DB && v >= 0 && (n == 2048 || n == 4096)) {
                 std::vector<float4> t(k1m_table_f4((int)n));
                 k1m_build_tables((int)n, nullptr, 0.0, 0.0, t.data());
                 K1WParams dummy{};
@@ -612,7 +586,7 @@ kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint
                 if (env && v == 301) p->k1m_wink = window == KOPEK_WINDOW_RECT ? 0 : 1;    // tuning: table window
                 if ((e = cudaMalloc(&p->d_k1m, sizeof(float4) * t.size())) != cudaSuccess ||
                     (e = cudaMemcpy(p->d_k1m, t.data(), sizeof(float4) * t.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
-                    (e = k1m_launch((int)n, dummy, (int)output, p->k1m_wink, 0, nullptr,
+                    (e = k1m_launch((int)n, dummy, (int)output, p->k1m_wink, 0, 0, nullptr,
                                     &p->k1m_teams_per_sm)) != cudaSuccess ||
                     p->k1m_teams_per_sm <= 0) {
                     st = fail(KOPEK_ERR_CUDA, "K1M-%u setup failed: %s", n, cudaGetErrorString(e));
@@ -685,10 +659,11 @@ uint32_t kopek_plan_last_launches(const kopek_plan *plan) { return plan ? plan->
 
 static kopek_status stft_launch(const kopek_plan *plan, const float *d_samples, uint64_t frames, void *d_out,
                                 cudaStream_t stream) {
-    if (plan->output >= KOPEK_OUT_BANDS_LOG && (uintptr_t)d_samples % 16 != 0)
-        return fail(KOPEK_ERR_INVALID, "band epilogues need a 16-byte aligned sample buffer");
-    if (plan->d_k1w && (plan->n == 256 || plan->n == 512) && plan->bins_mode == KOPEK_BINS_HALF && plan->hop % 4 == 0 &&
-        (uintptr_t)d_samples % 16 == 0) {
+    if (plan->d_k1w && (plan->n == 256 || plan->n == 512)) {
+        // sub-warp kernels: HALF or FULL rows, any hop, any 4-byte aligned base
+        const uint32_t need = plan->n == 256 ? 4 : 2;          // 128-bit (256) / 64-bit (512) vector loads
+        const bool vecl = plan->hop % need == 0 && (uintptr_t)d_samples % (4 * need) == 0;
+        const int mode = (plan->bins_mode == KOPEK_BINS_FULL ? 1 : 0) + (vecl ? 0 : 2);
         K1WParams wp{};
         wp.x = d_samples;
         wp.out = d_out;
@@ -702,27 +677,34 @@ static kopek_status stft_launch(const kopek_plan *plan, const float *d_samples, 
         const uint64_t warps = (uint64_t)plan->sm_count * plan->k1w_warps_per_sm;
         const int grid = (int)std::min<uint64_t>((groups + 3) / 4, warps / 4);
         const bool win = plan->window != KOPEK_WINDOW_RECT;
-        cudaError_t e = plan->n == 256 ? k1w256_launch(wp, (int)plan->output, win, grid, stream, nullptr)
-                                       : k1w512_launch(wp, (int)plan->output, win, grid, stream, nullptr);
+        cudaError_t e = plan->n == 256 ? k1w256_launch(wp, (int)plan->output, win, mode, grid, stream, nullptr)
+                                       : k1w512_launch(wp, (int)plan->output, win, mode, grid, stream, nullptr);
         if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "K1W-%u launch failed: %s", plan->n, cudaGetErrorString(e));
         return KOPEK_OK;
     }
-    if (plan->d_k1m && plan->bins_mode == KOPEK_BINS_HALF && plan->hop % 2 == 0 && (uintptr_t)d_samples % 8 == 0) {
-        K1WParams wp{};
-        wp.x = d_samples;
-        wp.out = d_out;
-        wp.tables = plan->d_k1m;
-        wp.n_frames = frames;
-        wp.hop = plan->hop;
-        wp.pitch = plan->pitch;
-        wp.band_scale = 1.0f;
-        const int grid = (int)std::min<uint64_t>(frames, (uint64_t)plan->sm_count * plan->k1m_teams_per_sm);
-        cudaError_t e = k1m_launch((int)plan->n, wp, (int)plan->output, plan->k1m_wink, grid, stream, nullptr);
-        if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "K1M-%u launch failed: %s", plan->n, cudaGetErrorString(e));
-        return KOPEK_OK;
+    {
+        // team-per-frame kernels (2048 / 4096 points): HALF or FULL rows, any hop, any 4-byte aligned base; only a
+        // custom window table combined with FULL rows or unaligned frames is left to the generic kernel
+        const bool vec = plan->hop % 2 == 0 && (uintptr_t)d_samples % 8 == 0;
+        const int mode = (plan->bins_mode == KOPEK_BINS_FULL ? 1 : 0) + (vec ? 0 : 2);
+        if (plan->d_k1m && (mode == 0 || plan->k1m_wink != 1)) {
+            K1WParams wp{};
+            wp.x = d_samples;
+            wp.out = d_out;
+            wp.tables = plan->d_k1m;
+            wp.n_frames = frames;
+            wp.hop = plan->hop;
+            wp.pitch = plan->pitch;
+            wp.band_scale = 1.0f;
+            wp.vec = vec ? 1u : 0u;
+            const int grid = (int)std::min<uint64_t>(frames, (uint64_t)plan->sm_count * plan->k1m_teams_per_sm);
+            cudaError_t e = k1m_launch((int)plan->n, wp, (int)plan->output, plan->k1m_wink, mode, grid, stream, nullptr);
+            if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "K1M-%u launch failed: %s", plan->n, cudaGetErrorString(e));
+            return KOPEK_OK;
+        }
     }
-    if ((plan->d_k1b || plan->d_k1w) && plan->n == 1024 && plan->bins_mode == KOPEK_BINS_HALF && plan->hop % 4 == 0 &&
-        (uintptr_t)d_samples % 16 == 0) {
+    if (plan->d_k1b && plan->n == 1024) {
+        // every 1024-point mode runs on the two-exchange kernel: HALF or FULL rows, any hop, any 4-byte aligned base
         K1WParams wp{};
         wp.x = d_samples;
         wp.out = d_out;
@@ -731,28 +713,21 @@ static kopek_status stft_launch(const kopek_plan *plan, const float *d_samples, 
         wp.hop = plan->hop;
         wp.pitch = plan->pitch;
         wp.band_scale = plan->band_scale;
-        // bulk-store epilogue: opt-in, f32 spectra, 16-byte aligned rows (else the direct 32-bit stores)
-        const bool bulk = plan->bulk_store && plan->output >= KOPEK_OUT_MAG && plan->output <= KOPEK_OUT_DB &&
-                          plan->pitch % 4 == 0 && (uintptr_t)d_out % 16 == 0;
-        if (plan->d_k1b) {
-            const uint64_t warps_b = (uint64_t)plan->sm_count * plan->k1b_warps_per_sm;
-            const int grid_b = (int)std::min<uint64_t>((frames + 3) / 4, warps_b / 4);
-            cudaError_t eb = k1b_launch(wp, (int)plan->output, plan->window != KOPEK_WINDOW_RECT, bulk, grid_b, stream,
-                                        nullptr);
-            if (eb != cudaSuccess) return fail(KOPEK_ERR_CUDA, "K1W-1024b launch failed: %s", cudaGetErrorString(eb));
-            return KOPEK_OK;
+        wp.vec = (plan->hop % 2 == 0 && (uintptr_t)d_samples % 8 == 0) ? 1u : 0u;
+        const uint64_t warps_b = (uint64_t)plan->sm_count * plan->k1b_warps_per_sm;
+        const int grid_b = (int)std::min<uint64_t>((frames + 3) / 4, warps_b / 4);
+        const bool win = plan->window != KOPEK_WINDOW_RECT;
+        cudaError_t eb;
+        if (plan->bins_mode == KOPEK_BINS_FULL) {
+            eb = k1b_launch_full(wp, (int)plan->output, win, grid_b, stream);
+        } else {
+            // bulk-store epilogue: opt-in, f32 spectra, 16-byte aligned rows (else the direct 32-bit stores)
+            const bool bulk = plan->bulk_store && wp.vec && plan->output >= KOPEK_OUT_MAG && plan->output <= KOPEK_OUT_DB &&
+                              plan->pitch % 4 == 0 && (uintptr_t)d_out % 16 == 0;
+            eb = k1b_launch(wp, (int)plan->output, win, bulk, grid_b, stream, nullptr);
         }
-#ifdef KOPEK_K1W_SWEEP
-        wp.tables = plan->d_k1w;
-        const int variant = bulk ? 100 : plan->k1w_variant;
-        const uint64_t warps = (uint64_t)plan->sm_count * plan->k1w_warps_per_sm;
-        const int wpb = k1w_variant_warps(variant);
-        const int grid = (int)std::min<uint64_t>((frames + wpb - 1) / wpb, warps / wpb);
-        cudaError_t e = k1w_launch(wp, (int)plan->output, plan->window != KOPEK_WINDOW_RECT, variant, grid, stream,
-                                   nullptr);
-        if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "K1W launch failed: %s", cudaGetErrorString(e));
+        if (eb != cudaSuccess) return fail(KOPEK_ERR_CUDA, "K1W-1024b launch failed: %s", cudaGetErrorString(eb));
         return KOPEK_OK;
-#endif
     }
     K1Params kp;
     kp.x = d_samples;

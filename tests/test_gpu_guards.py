@@ -103,4 +103,6 @@ def test_exec_host_chunks_are_sized_by_the_busier_direction(built_lib):
         assert used < (1 << 30), f"chunk slots took {used >> 20} MiB"
         with StftPlan(n, 1024, 1, 1) as coarse:
             ref = coarse.exec_host(x)
-        assert np.array_equal(got[::1024], ref)
+        # every 1024th frame is a frame of the coarse plan (another kernel: same values to rounding)
+        assert got.shape[0] == 20001 and ref.shape[0] == 20
+        assert np.abs(got[::1024][:20] - ref).max() <= 1e-5 * 12 * ref.max()

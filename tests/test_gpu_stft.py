@@ -313,3 +313,64 @@ def test_window_is_accurate_sample_by_sample(built_lib, oracle_mod, n, window):
             assert np.abs(got[f]).max() <= 1e-9, p
         else:
             assert np.abs(got[f] - ref).max() <= tol(n) * ref, (p, got[f, :3], ref)
+
+
+@pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("output,window", [(0, 0), (1, 1), (3, 2), (2, 0)])
+def test_full_rows_every_size(built_lib, oracle_mod, n, output, window):
+    """All N bins per row, as the reference's callers iterate them (examples/graph/utils.rs:47-63): the lane-group
+    kernels store the conjugate mirror beside the computed half.  Held to the oracle's full-length spectrum, to exact
+    mirror symmetry, and to the guard values around every row (pitch > N)."""
+    from kopek_b200 import BINS_FULL, StftPlan, signals
+    hop = n // 2 + 4
+    x = signals.white_noise(n + hop * 37, seed=n + output) + 0.5
+    with StftPlan(n, hop, window, output, BINS_FULL, out_pitch=n + 8) as plan:
+        assert plan.bins == n and plan.pitch == n + 8
+        raw = _run(plan, x)
+    assert np.isnan(raw[:, n:].real).all(), "wrote into the row padding"
+    got = raw[:, :n]
+    ref = oracle_mod.stft_complex(x, n, hop, window, bins=n)
+    if output == 0:
+        assert frame_rel_err(got.astype(np.complex128), ref) <= tol(n)
+        assert np.array_equal(got[:, 1:n // 2], np.conj(got[:, :n // 2:-1]))           # X[N - k] == conj X[k], bit for bit
+    else:
+        lin = np.abs(ref)
+        g = got.astype(np.float64)
+        g = 10.0 ** (g / 20.0) if output == 3 else np.sqrt(g) if output == 2 else g
+        assert (np.abs(g - lin) / lin.max(axis=1, keepdims=True)).max() <= tol(n)
+        assert np.array_equal(got[:, 1:n // 2], got[:, :n // 2:-1])
+
+
+@pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("hop_kind", ["odd", "two_mod_four"])
+def test_unaligned_frames_every_size(built_lib, oracle_mod, n, hop_kind, monkeypatch):
+    """Odd hops and base pointers that are only 4-byte aligned run on the lane-group kernels with 32-bit loads: same
+    values as the vector-load instantiation (bit for bit, on an aligned copy of the same samples) and within tolerance
+    of the oracle and of the generic kernel."""
+    import torch
+    from kopek_b200 import StftPlan, signals
+    hop = n // 4 + (3 if hop_kind == "odd" else 2)
+    frames = 53
+    x = signals.chirp((frames - 1) * hop + n + 3, 48000.0, 30.0, 21000.0) + 0.01 * signals.white_noise((frames - 1) * hop + n + 3, 3)
+    dx = torch.from_numpy(x).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    with StftPlan(n, hop, 1, 1) as plan:
+        out = torch.full((frames, plan.pitch), float("nan"), device="cuda")
+        # base shifted by one sample: 4-byte aligned only
+        assert plan.exec_ptr(dx.data_ptr() + 4, (frames - 1) * hop + n, out.data_ptr(), st) == frames
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+    ref = oracle_mod.stft_mag(x[1:], n, hop, 1)[:frames]
+    assert (np.abs(got - ref) / ref.max(axis=1, keepdims=True)).max() <= tol(n)
+    # frame by frame on an aligned copy (hop = n: the vector-load instantiation): identical bits
+    fr = np.stack([x[1 + f * hop: 1 + f * hop + n] for f in range(frames)]).reshape(-1)
+    with StftPlan(n, n, 1, 1) as vplan:
+        same = _run(vplan, fr)
+    assert np.array_equal(got.view(np.uint32), same.view(np.uint32))
+    # the generic kernel (cross-check build of the same plan)
+    monkeypatch.setenv("KOPEK_K1W_VARIANT", "-1")
+    with StftPlan(n, hop, 1, 1) as gplan:
+        gen = torch.full((frames, gplan.pitch), float("nan"), device="cuda")
+        gplan.exec_ptr(dx.data_ptr() + 4, (frames - 1) * hop + n, gen.data_ptr(), st)
+        torch.cuda.synchronize()
+    assert (np.abs(gen.cpu().numpy() - ref) / ref.max(axis=1, keepdims=True)).max() <= tol(n)
