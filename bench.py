@@ -49,7 +49,7 @@ ALGO_BYTES_PER_FRAME = N_FFT * 4 + BINS * 4          # 6148: samples read once +
 METRIC = "complex samples/sec batched 1024-pt FFT+mag"
 UNIT = "samples/s"
 WORKLOAD = "M: 2^20 frames x 1024-pt real f32 per GPU, Hann window, |X| (513 f32/frame), non-overlapping"
-HEADLINE_KERNEL_SOURCES = ("fft_warp1024b.cuh", "fft_warp512.cuh", "fft_warp1024.cuh", "fft_batched.cuh", "k1w_inst.cu")
+HEADLINE_KERNEL_SOURCES = ("fft_warp1024b.cuh", "fft_warp512.cuh", "fft_warp256.cuh", "lane_common.cuh", "fft_batched.cuh", "k1w_inst.cu")
 L2_BYTES = 126 << 20
 
 

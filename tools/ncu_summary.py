@@ -79,10 +79,14 @@ def full(rep, out, js=None):
             v = float(r[i].replace(",", ""))
             return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(units[i], 1.0)
         r = data[-1]
+        import os
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        import bench                       # the hash of the kernel's sources: bench.py quotes the capture only for this build
         with open(js, "w") as f:
             json.dump({"dram_bytes_per_launch": val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum"),
                        "dram_read": val(r, "dram__bytes_read.sum"), "dram_write": val(r, "dram__bytes_write.sum"),
-                       "kernel": r[hdr.index("Kernel Name")][:100], "source": rep}, f)
+                       "kernel": r[hdr.index("Kernel Name")][:100], "source": rep,
+                       "kernel_src_sha": bench.headline_kernel_fingerprint()}, f)
 
 
 if __name__ == "__main__":
