@@ -49,7 +49,7 @@ ALGO_BYTES_PER_FRAME = N_FFT * 4 + BINS * 4          # 6148: samples read once +
 METRIC = "complex samples/sec batched 1024-pt FFT+mag"
 UNIT = "samples/s"
 WORKLOAD = "M: 2^20 frames x 1024-pt real f32 per GPU, Hann window, |X| (513 f32/frame), non-overlapping"
-HEADLINE_KERNEL_SOURCES = ("fft_warp1024b.cuh", "fft_warp512.cuh", "fft_warp256.cuh", "lane_common.cuh", "fft_batched.cuh", "k1w_inst.cu")
+HEADLINE_KERNEL_SOURCES = ("fft_warp1024b.cuh", "lane_common.cuh", "fft_batched.cuh", "k1w_inst.cu")
 L2_BYTES = 126 << 20
 
 
@@ -308,22 +308,37 @@ def copy_ceiling(c, in_bytes: int, out_bytes: int, reps: int = 3):
     d_out = torch.empty(out_bytes, dtype=torch.uint8, device=c.device)
     s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
 
-    def once():
+    chunk = 16 << 20
+
+    def whole():
         with torch.cuda.stream(s1):
             d_in.copy_(h_in, non_blocking=True)
         with torch.cuda.stream(s2):
             h_out.copy_(d_out, non_blocking=True)
+
+    def chunked():                         # the shape of the e2e leg's traffic: 16 MiB pieces in both directions
+        for off in range(0, in_bytes, chunk):
+            with torch.cuda.stream(s1):
+                d_in[off:off + chunk].copy_(h_in[off:off + chunk], non_blocking=True)
+            o0, o1 = off * out_bytes // in_bytes, min(out_bytes, (off + chunk) * out_bytes // in_bytes)
+            with torch.cuda.stream(s2):
+                h_out[o0:o1].copy_(d_out[o0:o1], non_blocking=True)
+
+    best = 0.0
+    for once in (whole, chunked):
+        once()
         s1.synchronize()
         s2.synchronize()
-
-    once()
-    c.barrier()
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        once()
-    c.barrier()
-    dt = max_over_ranks(c, time.perf_counter() - t0)
-    return c.world * (in_bytes / 4) * reps / dt
+        c.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            once()
+            s1.synchronize()
+            s2.synchronize()
+        c.barrier()
+        dt = max_over_ranks(c, time.perf_counter() - t0)
+        best = max(best, c.world * (in_bytes / 4) * reps / dt)
+    return best
 
 
 def bench_config_cfg0(c):
@@ -554,8 +569,9 @@ def run_ours(args):
                     "matches_device_result": same,
                     "api": "kopek_stft_exec_host (pinned host buffers, chunked H2D/kernel/D2H on 3 streams)",
                     "copy_ceiling": ceiling, "frac_of_copy_ceiling": e2e_value / ceiling,
-                    "copy_ceiling_how": "every rank at once: one pinned H2D cudaMemcpyAsync of the step's input and one "
-                                        "D2H of its output on two streams, no kernel (max over ranks)",
+                    "copy_ceiling_how": "every rank at once, no kernel: the step's input H2D and its output D2H from pinned "
+                                        "buffers on two streams, as one copy per direction and as 16 MiB pieces -- the "
+                                        "better of the two (max over ranks)",
                     "cpus_near_gpu": near},
             "gpu_launches": launches,
             "clocks": clocks,

@@ -99,7 +99,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False, 
         obj = os.path.join(OBJ, f"k1m_{r}.o")
         jobs.append((obj, [cc, *ARCH, *COMMON, *extra, f"-DKOPEK_K1M_R={r}", "-c", os.path.join(CSRC, "k1m_inst.cu"),
                            "-o", obj]))
-    for name in ("kopek_cuda", "k1w_inst", "fft_large", "synth", "pcm", "dist_fft", "mgpu"):
+    for name in ("kopek_cuda", "k1w_inst", "k1w_small_inst", "fft_large", "synth", "pcm", "dist_fft", "mgpu"):
         src = os.path.join(CSRC, name + ".cu")
         if os.path.exists(src):
             obj = os.path.join(OBJ, name + ".o")

@@ -21,7 +21,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "fft_warp512.cuh"
+#include "lane_common.cuh"
 
 namespace kopek {
 

@@ -36,5 +36,42 @@ inline void show(const std::string &label, const std::vector<std::complex<double
     if (st != KOPEK_OK) throw std::runtime_error(std::string("kopek::fft::show: ") + kopek_last_error());
 }
 
+// kopek::fft::stft_magnitude / stft_magnitude_multi of rust/kopek/src/fft.rs: many frames per call through the fused
+// window -> real FFT -> |X| plan, on one device or sharded over several from this one process (kopek_mgpu_*).
+inline std::vector<std::vector<float>> stft_magnitude(const std::vector<float> &samples, uint32_t n, uint32_t hop, bool hann) {
+    kopek_plan *plan = nullptr;
+    if (kopek_plan_create(&plan, n, hop, hann ? KOPEK_WINDOW_HANN : KOPEK_WINDOW_RECT, KOPEK_OUT_MAG, KOPEK_BINS_HALF, 0,
+                          0) != KOPEK_OK)
+        throw std::runtime_error(std::string("kopek::fft::stft_magnitude: ") + kopek_last_error());
+    const size_t frames = kopek_plan_frames(plan, samples.size()), bins = kopek_plan_bins(plan);
+    std::vector<float> flat(frames * bins);
+    uint64_t got = 0;
+    kopek_status st = kopek_stft_exec_host(plan, samples.data(), samples.size(), flat.data(), &got);
+    kopek_plan_destroy(plan);
+    if (st != KOPEK_OK) throw std::runtime_error(std::string("kopek::fft::stft_magnitude: ") + kopek_last_error());
+    std::vector<std::vector<float>> rows(frames);
+    for (size_t f = 0; f < frames; ++f) rows[f].assign(flat.begin() + f * bins, flat.begin() + (f + 1) * bins);
+    return rows;
+}
+
+inline std::vector<std::vector<float>> stft_magnitude_multi(const std::vector<float> &samples, uint32_t n, uint32_t hop,
+                                                            bool hann, const std::vector<int32_t> &devices) {
+    kopek_mgpu *ctx = nullptr;
+    if (kopek_mgpu_create(&ctx, devices.data(), (uint32_t)devices.size(), n, hop, hann ? KOPEK_WINDOW_HANN : KOPEK_WINDOW_RECT,
+                          KOPEK_OUT_MAG, KOPEK_BINS_HALF, 0) != KOPEK_OK)
+        throw std::runtime_error(std::string("kopek::fft::stft_magnitude_multi: ") + kopek_last_error());
+    const size_t bins = kopek_mgpu_bins(ctx);
+    const size_t frames = samples.size() < n ? 0 : 1 + (samples.size() - n) / hop;
+    std::vector<float> flat(frames * bins);
+    uint64_t got = 0;
+    kopek_status st = kopek_mgpu_exec_host(ctx, samples.data(), samples.size(), flat.data(), &got);
+    std::string msg = st != KOPEK_OK ? kopek_last_error() : "";
+    kopek_mgpu_destroy(ctx);
+    if (st != KOPEK_OK) throw std::runtime_error("kopek::fft::stft_magnitude_multi: " + msg);
+    std::vector<std::vector<float>> rows(frames);
+    for (size_t f = 0; f < frames; ++f) rows[f].assign(flat.begin() + f * bins, flat.begin() + (f + 1) * bins);
+    return rows;
+}
+
 }  // namespace fft
 }  // namespace kopek

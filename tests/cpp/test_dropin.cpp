@@ -37,6 +37,20 @@ int main() {
         oracle_fft_f64(reinterpret_cast<const double *>(x.data()), n_in, reinterpret_cast<double *>(r.data()));
         if (y.size() != r.size() || memcmp(y.data(), r.data(), r.size() * sizeof(r[0])) != 0) { printf("n_in=%zu mismatch\n", n_in); ++bad; }
     }
+    // many frames at once, one device and every visible device from this one process (kopek_mgpu_*): identical bits
+    {
+        std::vector<float> sig(48000);
+        for (size_t i = 0; i < sig.size(); ++i) sig[i] = (float)sin(2.0 * M_PI * 440.0 * (double)i / 48000.0) + 0.25f * (float)cos(0.01 * i * i);
+        std::vector<std::vector<float>> one = kopek::fft::stft_magnitude(sig, 1024, 256, true);
+        std::vector<int32_t> devs;
+        for (int d = 0; d < kopek_device_count() && d < 8; ++d) devs.push_back(d);
+        std::vector<std::vector<float>> many = kopek::fft::stft_magnitude_multi(sig, 1024, 256, true, devs);
+        bool same = one.size() == many.size() && one.size() == 1 + (sig.size() - 1024) / 256;
+        for (size_t f = 0; same && f < one.size(); ++f)
+            same = one[f].size() == 513 && memcmp(one[f].data(), many[f].data(), 513 * sizeof(float)) == 0;
+        printf("stft_magnitude_multi over %zu device(s): %s\n", devs.size(), same ? "identical" : "MISMATCH");
+        if (!same) ++bad;
+    }
     kopek::fft::show("spectrum", std::vector<std::complex<double>>(out.begin(), out.begin() + 3));
     printf(bad ? "DROPIN_FAIL\n" : "DROPIN_OK\n");
     return bad;

@@ -43,15 +43,18 @@ def timed(fn, iters=20, warm=3):
 rows = []
 
 
-def stft_case(name, n, hop, window, output, n_samples, gen=None):
-    x = torch.randn(n_samples, device="cuda") if gen is None else torch.from_numpy(gen).cuda()
-    plan = StftPlan(n, hop, window, output)
+def stft_case(name, n, hop, window, output, n_samples, gen=None, bins=0, offset=0):
+    """offset: samples skipped at the start of the buffer (1 = a base pointer that is only 4-byte aligned)."""
+    x = torch.randn(n_samples + offset, device="cuda") if gen is None else torch.from_numpy(gen).cuda()
+    plan = StftPlan(n, hop, window, output, bins=bins)
     frames = plan.frames(n_samples)
     out = torch.empty((frames, plan.pitch), device="cuda")
-    ms = timed(lambda: plan.exec_ptr(x.data_ptr(), n_samples, out.data_ptr(), st))
-    by = n_samples * 4 + frames * plan.bins * 4
+    time.sleep(1.0)                      # every row starts from a cooled board: burst figures, comparable between rows
+    ms = timed(lambda: plan.exec_ptr(x.data_ptr() + 4 * offset, n_samples, out.data_ptr(), st))
+    by = ((frames - 1) * hop + n) * 4 + frames * plan.bins * 4
     rows.append((name, f"{frames} frames", ms, by, frames * n / ms / 1e6))
     plan.close()
+    del x, out
 
 
 # M
@@ -67,6 +70,21 @@ stft_case("512-pt: 2^21 x 512 Hann |X| (K1W-512)", 512, 512, WINDOW_HANN, OUT_MA
 stft_case("2048-pt: 2^19 x 2048 Hann |X| (K1M)", 2048, 2048, WINDOW_HANN, OUT_MAG, (1 << 19) * 2048)
 stft_case("4096-pt: 2^18 x 4096 Hann |X| (K1M)", 4096, 4096, WINDOW_HANN, OUT_MAG, (1 << 18) * 4096)
 stft_case("1024-pt STFT hop 256: 2^28 samples Hann |X| (K1W-b)", 1024, 256, WINDOW_HANN, OUT_MAG, 1 << 28)
+# what the reference's callers iterate: ALL N bins per row (examples/graph/utils.rs:47-63) -- round 2: on the lane-group kernels
+stft_case("FULL rows 1024: 2^20 x 1024 rect |X|, 1024 bins/row (K1W-b)", 1024, 1024, WINDOW_RECT, OUT_MAG, (1 << 20) * 1024, bins=1)
+stft_case("FULL rows 256: 2^22 x 256 rect |X| (K1W-256)", 256, 256, WINDOW_RECT, OUT_MAG, (1 << 22) * 256, bins=1)
+stft_case("FULL rows 512: 2^21 x 512 Hann |X| (K1W-512)", 512, 512, WINDOW_HANN, OUT_MAG, (1 << 21) * 512, bins=1)
+stft_case("FULL rows 2048: 2^19 x 2048 Hann |X| (K1M)", 2048, 2048, WINDOW_HANN, OUT_MAG, (1 << 19) * 2048, bins=1)
+stft_case("FULL rows 4096: 2^18 x 4096 Hann |X| (K1M)", 4096, 4096, WINDOW_HANN, OUT_MAG, (1 << 18) * 4096, bins=1)
+# odd hops / a base pointer that is only 4-byte aligned (32-bit loads on the same kernels)
+stft_case("odd hop 1023, 1024-pt Hann |X| (K1W-b, 32-bit loads)", 1024, 1023, WINDOW_HANN, OUT_MAG, (1 << 20) * 1023 + 1)
+stft_case("unaligned base (+1 sample), 1024-pt Hann |X| (K1W-b)", 1024, 1024, WINDOW_HANN, OUT_MAG, (1 << 20) * 1024, offset=1)
+stft_case("odd hop 2047, 2048-pt Hann |X| (K1M, 32-bit loads)", 2048, 2047, WINDOW_HANN, OUT_MAG, (1 << 19) * 2047 + 1)
+stft_case("odd hop 4095, 4096-pt Hann |X| (K1M, 32-bit loads)", 4096, 4095, WINDOW_HANN, OUT_MAG, (1 << 18) * 4095 + 1)
+stft_case("odd hop 255, 256-pt rect |X| (K1W-256, 32-bit loads)", 256, 255, WINDOW_RECT, OUT_MAG, (1 << 22) * 255 + 1)
+# fused band epilogues (input bytes only)
+stft_case("bands LOG: 2^20 x 1024 Hann -> 10 f32/frame (K1W-b)", 1024, 1024, WINDOW_HANN, 4, (1 << 20) * 1024)
+stft_case("bands LOW: 2^20 x 1024 Hann -> 10 f32/frame (K1W-b)", 1024, 1024, WINDOW_HANN, 5, (1 << 20) * 1024)
 # the library bar on the headline shape: cuFFT R2C through torch.fft.rfft, then a separate |.| kernel,
 # window multiply included (three extra HBM round trips); reported beside the fused kernel, never part of the product
 lib_rows = []
@@ -84,6 +102,8 @@ for lg in (20, 22, 24):
     b = torch.empty_like(a)
     ms = timed(lambda: fft.fft_large_device(a.data_ptr(), b.data_ptr(), n, 0, st))
     rows.append((f"cfg3: single 2^{lg} c2c f32 four-step (K3)", "1 transform", ms, 2 * n * 8, n / ms / 1e6))
+    ms = timed(lambda: torch.fft.fft(a))
+    lib_rows.append((f"cuFFT C2C f32 (torch.fft.fft), single 2^{lg}", ms, 2 * n * 8, n / ms / 1e6))
 # decoder-side callers: i16 stereo frames as kopek::decoder::decode returns them
 dec_rows = []
 nfr = 1 << 28

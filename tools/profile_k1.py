@@ -21,11 +21,12 @@ ap.add_argument("--output", type=int, default=1)
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--pitch", type=int, default=0)
 ap.add_argument("--bulk", action="store_true")
+ap.add_argument("--full", action="store_true", help="all n bins per row")
 a = ap.parse_args()
 hop = a.hop or a.n
 ns = (a.frames - 1) * hop + a.n
 x = torch.randn(ns, device="cuda")
-plan = StftPlan(a.n, hop, a.window, a.output, out_pitch=a.pitch, bulk_store=a.bulk)
+plan = StftPlan(a.n, hop, a.window, a.output, bins=1 if a.full else 0, out_pitch=a.pitch, bulk_store=a.bulk)
 out = torch.empty((a.frames, plan.pitch), device="cuda", dtype=torch.complex64 if a.output == 0 else torch.float32)
 st = torch.cuda.current_stream().cuda_stream
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
