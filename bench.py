@@ -51,6 +51,36 @@ UNIT = "samples/s"
 WORKLOAD = "M: 2^20 frames x 1024-pt real f32 per GPU, Hann window, |X| (513 f32/frame), non-overlapping"
 HEADLINE_KERNEL_SOURCES = ("fft_warp1024b.cuh", "lane_common.cuh", "fft_batched.cuh", "k1w_inst.cu")
 L2_BYTES = 126 << 20
+# Static instruction mix of the frame loop of the kernels the configs run on, per LANE and frame (tools/loop_mix.py on the
+# shipped build; tests/test_kernel_models.py::test_bench_static_mix_matches_the_library keeps them in step): the
+# overlapped STFT configs transform every sample N/hop times, so their roofs are FP32 throughput and instruction issue,
+# not HBM.  flops: FFMA and the packed FADD2 count 2, FADD / FMUL 1.
+KERNEL_MIX = {
+    "k1w_1024b<MAG,WIN>": {"symbol": "k1w_1024b_kernelILi1ELb1ELi4ELi3ELb0ELb0ELb0ELb1E", "lanes": 32, "loop": 789,
+                           "FFMA": 207, "FMUL": 112, "FADD": 273, "FADD2": 0},
+    "k1m<4,DB,cos-sum>": {"symbol": "k1m_kernelILi4ELi3ELi2ELi6ELi0ELb0ELb1E", "lanes": 64, "loop": 828,
+                          "FFMA": 242, "FMUL": 144, "FADD": 141, "FADD2": 108},
+    "k1m<8,MAG,cos-sum>": {"symbol": "k1m_kernelILi8ELi1ELi2ELi3ELi0ELb0ELb1E", "lanes": 128, "loop": 897,
+                           "FFMA": 249, "FMUL": 180, "FADD": 135, "FADD2": 124},
+}
+SM_COUNT, FP32_LANES_PER_SM, SCHEDULERS_PER_SM = 148, 128, 4
+
+
+def compute_roofs(mix_key: str, frames: int, ms: float, sm_mhz: float):
+    """FP32 and instruction-issue roofs of one launch at the SM clock `sm_mhz` (the board's maximum: an upper bound)."""
+    m = KERNEL_MIX[mix_key]
+    flops = m["lanes"] * (2 * m["FFMA"] + m["FMUL"] + m["FADD"] + 2 * m["FADD2"])
+    warp_instr = m["lanes"] // 32 * m["loop"]
+    fp32_peak = SM_COUNT * FP32_LANES_PER_SM * 2 * sm_mhz * 1e6
+    issue_peak = SM_COUNT * SCHEDULERS_PER_SM * sm_mhz * 1e6
+    t = ms * 1e-3
+    return {"kernel_mix": mix_key, "flops_per_frame": flops, "warp_instructions_per_frame": warp_instr,
+            "fp32": {"achieved_tflops": frames * flops / t / 1e12, "peak_tflops": fp32_peak / 1e12,
+                     "frac": frames * flops / t / fp32_peak},
+            "issue": {"achieved_ginstr_s": frames * warp_instr / t / 1e9, "peak_ginstr_s": issue_peak / 1e9,
+                      "frac": frames * warp_instr / t / issue_peak},
+            "clock_mhz": sm_mhz, "note": "static SASS mix of the frame loop (profiles/r2_sass_summary.md); peaks at the "
+                                         "board's maximum SM clock"}
 
 
 def _peaks():
@@ -561,6 +591,8 @@ def run_ours(args):
                          "kernel": "k1w_1024b_kernel<MAG,WIN> (warp per frame, two shared-memory exchanges, LDG register prefetch)",
                          "kernel_src_sha": headline_kernel_fingerprint(), "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": frames * ALGO_BYTES_PER_FRAME,
+                         "compute_roofs": compute_roofs("k1w_1024b<MAG,WIN>", frames, kernel_ms,
+                                                        float(clocks.get("sm_max_mhz") or 1965.0)),
                          "sustained": None if sustained is None else dict(
                              sustained, frac=frames * ALGO_BYTES_PER_FRAME / (sustained["ms_per_step"] * 1e-3) / 1e9 / c.peak)},
             "parity": parity,
@@ -581,6 +613,7 @@ def run_ours(args):
 
     # =============================================================== every BASELINE.json config ================
     configs = {}
+    sm_max = float(clocks.get("sm_max_mhz") or 1965.0)
     if not args.no_configs:
         if rank == 0:
             import oracle
@@ -594,6 +627,7 @@ def run_ours(args):
             "cfg1: 60 s x 48 kHz chirp 20 Hz -> 20 kHz, Hann 2048 / hop 512, dB, 1 GPU (5622 frames)",
             check_frames=5622, reps=200, copies=8)
         configs["cfg1"]["note"] = "34.6 MB per launch: launch/latency bound, the roofline fraction is not the figure of merit"
+        configs["cfg1"]["compute_roofs"] = compute_roofs("k1m<4,DB,cos-sum>", 5622, configs["cfg1"]["ms"], sm_max)
         del chirp
         # cfg2: 1 000 000 x 256-point white noise |X|, STRONG-scaled: rank r owns frames [r F / R, (r + 1) F / R)
         F2 = 1_000_000
@@ -621,6 +655,7 @@ def run_ours(args):
                                "k1m_kernel<8> (128 lanes per frame)",
                                f"cfg4: 8 h x 48 kHz x {world} channel(s) (one per GPU), Hann 4096 / hop 1024, |X|: "
                                f"{frames4} frames x 2049 bins per channel", check_frames=64, reps=5)
+        r4["compute_roofs"] = compute_roofs("k1m<8,MAG,cos-sum>", frames4, r4["ms"], sm_max)
         r4["channels"] = world
         r4["job_transformed_samples_per_s"] = r4["transformed_samples_per_s"] * world
         r4["fp32_note"] = ("hop = N/4: every sample is transformed 4 times, so this shape is bound by FP32 issue, not by "

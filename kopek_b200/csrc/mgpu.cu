@@ -139,8 +139,9 @@ static void mgpu_free(kopek_mgpu *c) {
 static kopek_status ensure_nccl(kopek_mgpu *c) {
     if (c->nccl_ready) return KOPEK_OK;
     NcclApi &nc = nccl_api();
-    if (!nc.ok) return fail(KOPEK_ERR_UNSUPPORTED, "NCCL gather: libnccl.so.2 could not be opened (%s)",
-                            dlerror() ? dlerror() : "symbols missing");
+    if (!nc.ok)
+        return fail(KOPEK_ERR_UNSUPPORTED, "NCCL gather: %s", nc.handle ? "libnccl.so.2 lacks the send/recv entry points"
+                                                                       : "libnccl.so.2 could not be opened (set KOPEK_NCCL_LIB)");
     const int R = (int)c->devs.size();
     std::vector<void *> comms(R, nullptr);
     std::vector<int> list(R);
