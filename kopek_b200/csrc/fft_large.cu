@@ -19,6 +19,7 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <mutex>
 #include <vector>
 
@@ -50,7 +51,7 @@ __host__ __device__ constexpr int k3_swz(int q) { return q ^ ((q >> 4) & 15); }
 struct K3NoOut {
     static constexpr bool enabled = false;
     __device__ __forceinline__ void reads_done() const {}
-    __device__ __forceinline__ void store(int, float2) const {}
+    __device__ __forceinline__ void store(int, bool, float2) const {}
 };
 
 // OUT (last stage only): instead of writing the result back to shared memory, `out.reads_done()` runs right after the
@@ -108,7 +109,7 @@ __device__ __forceinline__ void k3_stage(float2 *buf, const float2 *tw, int tid,
 #pragma unroll
         for (int k = 0; k < RAD; ++k) {
             int q = base + k * NS;
-            if constexpr (OUT::enabled) out.store(q, d[i * RAD + k]);
+            if constexpr (OUT::enabled) out.store(q, 2 * k >= RAD, d[i * RAD + k]);
             else buf[(WRITE_LINEAR ? q : k3_swz(q)) * COLS + c] = d[i * RAD + k];
         }
     }
@@ -146,6 +147,46 @@ __device__ __forceinline__ void tma_store_commit_wait() {
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// ---- L2 residency control (round 2) -------------------------------------------------------------------------------
+// `mid` is written by pass 1 and read once by pass 2.  The part of it that still sits in L2 when pass 2 starts needs
+// neither the HBM read nor -- if pass 2 drops the lines after reading them -- the HBM write-back.  Pass 1 therefore
+// stores the rows of mid it wants kept (all of them while mid fits, else the upper half of k1) with an evict_last
+// policy and the rest evict_first; pass 2 walks the tiles from the top, so that the kept rows come first, and
+// discards their lines once the tile is in shared memory (discard.global.L2: the line is dropped without write-back;
+// `mid` is dead after this read).  The INPUT stream keeps the normal policy: adjacent two-column tiles share 32-byte
+// sectors, and an evict_first line was gone before the neighbouring CTA read its half (+20 % DRAM reads, measured).
+// Measured (profiles/r2_k3_keep_sweep.txt): 2^22 0.0528 -> 0.0487 ms, 2^23 0.0841 -> 0.0785 ms, 2^24 0.1357 -> 0.1333 ms.
+// -DKOPEK_K3_NO_HINTS (tuning builds) compiles all of it away: plain stores, plain TMA loads, no discard.
+template <int KIND> __device__ __forceinline__ uint64_t l2_policy() {       // 1 evict_first, 2 evict_last
+    uint64_t p = 0;
+#ifndef KOPEK_K3_NO_HINTS
+    // not volatile: a policy is a constant the compiler may rematerialise instead of keeping it in registers
+    if constexpr (KIND == 1) asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    else asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+#endif
+    return p;
+}
+__device__ __forceinline__ void st_policy(float2 *ptr, float2 v, uint64_t pol) {
+#ifndef KOPEK_K3_NO_HINTS
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(ptr), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+#else
+    *ptr = v;
+#endif
+}
+__device__ __forceinline__ void l2_discard_line(const void *ptr) {
+#ifndef KOPEK_K3_NO_HINTS
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(ptr) : "memory");
+#endif
+}
+__device__ __forceinline__ void tma_load_1d_policy(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+#ifndef KOPEK_K3_NO_HINTS
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+#else
+    tma_load_1d(dst_smem, src_gmem, bytes, bar);
+#endif
+}
+
 struct K3Tables {
     const float2 *tw_sub1;   // per-stage t-major twiddles of the N1-point sub-transform (k3_stage_twiddles)
     const float2 *tw_sub2;   // same for N2
@@ -169,7 +210,9 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 
 // pass 1 output: thread (tid, c) holds A[k1][n2 = 2 s + c]; mid is tile-major [k1/4][n2/2][k1%4][n2%2], so the 16
 // lanes x 2 columns of a warp write four 64-byte segments per store instruction
-struct K3Out1 {
+// KEEP: which rows k1 of mid pass 1 asks L2 to hold until pass 2 has read them -- 0 none, 1 the upper half (the flag
+// `upper` is a compile-time property of the butterfly output after unrolling: no select, no compare), 2 all of them
+template <int KEEP> struct K3Out1 {
     static constexpr bool enabled = true;
     float2 *dst;               // mid + s * 8 + c
     size_t seg_stride;         // (N2 / 2) * 8 complex between k1/4 blocks
@@ -177,18 +220,22 @@ struct K3Out1 {
     const CUtensorMap *in_map;
     float2 *buf;
     int next_tile, n1;
+    uint64_t pol_keep, pol_stream;
     __device__ __forceinline__ void reads_done() const {
         if (threadIdx.x == 0 && next_tile >= 0) {
             mbar_expect_tx(bar, n1 * 16);
             for (int r0 = 0; r0 < n1; r0 += 256) tma_load_2d(buf + r0 * 2, in_map, 4 * next_tile, r0, bar);
         }
     }
-    __device__ __forceinline__ void store(int k1, float2 v) const { dst[(size_t)(k1 >> 2) * seg_stride + (k1 & 3) * 2] = v; }
+    __device__ __forceinline__ void store(int k1, bool upper, float2 v) const {
+        st_policy(dst + (size_t)(k1 >> 2) * seg_stride + (k1 & 3) * 2, v,
+                  (KEEP == 2 || (KEEP == 1 && upper)) ? pol_keep : pol_stream);
+    }
 };
 
 // ---- pass 1: column tiles s (columns 2s, 2s+1), all n1.  Two-column tiles (N1 x 16 B = 64 KB at N1 = 4096)
 // let TWO CTAs share an SM, so one transforms while the other waits on shared memory or on its TMA traffic.
-template <int N1>
+template <int N1, int KEEP>
 __global__ void __launch_bounds__(N1 / 8, 2)
 k3_pass1(const __grid_constant__ CUtensorMap in_map, float2 *__restrict__ mid, K3Tables tb, int n_tiles) {
     extern __shared__ __align__(128) unsigned char k3_smem[];
@@ -196,6 +243,7 @@ k3_pass1(const __grid_constant__ CUtensorMap in_map, float2 *__restrict__ mid, K
     float2 *s_tw = reinterpret_cast<float2 *>(k3_smem + (size_t)N1 * 16);   // stage twiddles, N1 entries
     uint64_t *bar = reinterpret_cast<uint64_t *>(k3_smem + (size_t)N1 * 24);
     for (int i = threadIdx.x; i < N1; i += N1 / 8) s_tw[i] = tb.tw_sub1[i];
+    const uint64_t pol_keep = l2_policy<2>(), pol_stream = l2_policy<1>();
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -212,7 +260,8 @@ k3_pass1(const __grid_constant__ CUtensorMap in_map, float2 *__restrict__ mid, K
         mbar_wait(bar, phase);
         phase ^= 1;
         const int nxt = s + gridDim.x;
-        K3Out1 out{mid + (size_t)s * 8 + c, (size_t)n_tiles * 8, bar, &in_map, buf, nxt < n_tiles ? nxt : -1, N1};
+        K3Out1<KEEP> out{mid + (size_t)s * 8 + c, (size_t)n_tiles * 8, bar, &in_map, buf, nxt < n_tiles ? nxt : -1, N1,
+                         pol_keep, pol_stream};
         // sub-transform + inter-step twiddle W_n^{n2 k1}, n2 = 2s + c (applied in registers before the stores)
         k3_fft_tile<2, N1, false, true>(buf, s_tw, tid, c, out, 2u * s + c, tb.tw_hi, tb.tw_lo);
     }
@@ -228,46 +277,55 @@ struct K3Out2 {
     const char *next_src;      // next tile's contiguous block of mid, or nullptr
     unsigned char *smem;
     int bytes, chunk;
+    uint64_t pol_load, pol_store;
     __device__ __forceinline__ void reads_done() const {
         if (threadIdx.x == 0 && next_src) {
             mbar_expect_tx(bar, bytes);
-            for (int off = 0; off < bytes; off += chunk) tma_load_1d(smem + off, next_src + off, chunk, bar);
+            for (int off = 0; off < bytes; off += chunk) tma_load_1d_policy(smem + off, next_src + off, chunk, bar, pol_load);
         }
     }
-    __device__ __forceinline__ void store(int k2, float2 v) const { dst[(size_t)k2 * n1] = v; }
+    __device__ __forceinline__ void store(int k2, bool, float2 v) const { st_policy(dst + (size_t)k2 * n1, v, pol_store); }
 };
 
 // ---- pass 2: row tiles u (rows k1 = 4u..4u+3), all n2; block mid[u] is contiguous
 template <int N2>
 __global__ void __launch_bounds__(N2 / 4, 1)
-k3_pass2(const float2 *__restrict__ mid, float2 *__restrict__ outp, K3Tables tb, int n_tiles) {
+k3_pass2(const float2 *__restrict__ mid, float2 *__restrict__ outp, K3Tables tb, int n_tiles, int keep_from_tile) {
     extern __shared__ __align__(128) unsigned char k3_smem[];
     float2 *buf = reinterpret_cast<float2 *>(k3_smem);
     float2 *s_tw = reinterpret_cast<float2 *>(k3_smem + (size_t)N2 * 32);
     uint64_t *bar = reinterpret_cast<uint64_t *>(k3_smem + (size_t)N2 * 40);
     for (int i = threadIdx.x; i < N2; i += N2 / 4) s_tw[i] = tb.tw_sub2[i];
     constexpr int CH = N2 * 32 < 16384 ? N2 * 32 : 16384;              // 1-D bulk copy granule
+    const uint64_t pol_stream = l2_policy<1>(), pol_normal = l2_policy<2>();    // kept tiles: stay until read, then dropped
+    // tiles are walked from the top: u = n_tiles - 1 - v, so the rows pass 1 asked L2 to keep are read first
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if ((int)blockIdx.x < n_tiles) {
+            const int u0 = n_tiles - 1 - (int)blockIdx.x;
             mbar_expect_tx(bar, N2 * 32);
-            const char *src = reinterpret_cast<const char *>(mid) + (size_t)blockIdx.x * N2 * 32;
-            for (int off = 0; off < N2 * 32; off += CH) tma_load_1d(k3_smem + off, src + off, CH, bar);
+            const char *src = reinterpret_cast<const char *>(mid) + (size_t)u0 * N2 * 32;
+            for (int off = 0; off < N2 * 32; off += CH)
+                tma_load_1d_policy(k3_smem + off, src + off, CH, bar, u0 >= keep_from_tile ? pol_normal : pol_stream);
         }
     }
     __syncthreads();
     const int c = threadIdx.x & 3, tid = threadIdx.x >> 2;
     const size_t n1 = (size_t)n_tiles * 4;
     uint32_t phase = 0;
-    for (int u = blockIdx.x; u < n_tiles; u += gridDim.x) {
+    for (int v = blockIdx.x; v < n_tiles; v += gridDim.x) {
+        const int u = n_tiles - 1 - v;
         mbar_wait(bar, phase);
         phase ^= 1;
-        const int nxt = u + gridDim.x;
+        // the tile is in shared memory: a kept tile's lines are dead in L2 (one line per thread: N2 * 32 / 128 = N2 / 4)
+        if (u >= keep_from_tile)
+            l2_discard_line(reinterpret_cast<const char *>(mid) + (size_t)u * N2 * 32 + (size_t)threadIdx.x * 128);
+        const int nv = v + gridDim.x, nu = n_tiles - 1 - nv;
         K3Out2 out{outp + 4 * (size_t)u + c, n1, bar,
-                   nxt < n_tiles ? reinterpret_cast<const char *>(mid) + (size_t)nxt * N2 * 32 : nullptr, k3_smem,
-                   N2 * 32, CH};
+                   nv < n_tiles ? reinterpret_cast<const char *>(mid) + (size_t)nu * N2 * 32 : nullptr, k3_smem,
+                   N2 * 32, CH, nu >= keep_from_tile ? pol_normal : pol_stream, pol_stream};
         k3_fft_tile<4, N2, true, false>(buf, s_tw, tid, c, out);
     }
 }
@@ -283,21 +341,25 @@ constexpr int K3R_TW_F2 = 63 * 64;                       // [t-1][kk] = W4096^{k
 constexpr int K3R_SMEM = K3R_EX_F2 * 8 + K3R_TW_F2 * 8 + 16;
 
 __global__ void __launch_bounds__(256, 1)
-k3_pass2_r64(const float2 *__restrict__ mid, float2 *__restrict__ outp, const float2 *__restrict__ tw_r64, int n_tiles) {
+k3_pass2_r64(const float2 *__restrict__ mid, float2 *__restrict__ outp, const float2 *__restrict__ tw_r64, int n_tiles,
+             int keep_from_tile) {
     extern __shared__ __align__(128) unsigned char k3_smem[];
     float2 *buf = reinterpret_cast<float2 *>(k3_smem);
     float2 *s_tw = buf + K3R_EX_F2;
     uint64_t *bar = reinterpret_cast<uint64_t *>(s_tw + K3R_TW_F2);
     for (int i = threadIdx.x; i < K3R_TW_F2; i += 256) s_tw[i] = tw_r64[i];
     constexpr int BYTES = K3R_TILE_F2 * 8, CH = 16384;
+    const uint64_t pol_stream = l2_policy<1>(), pol_normal = l2_policy<2>();
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if ((int)blockIdx.x < n_tiles) {
+            const int u0 = n_tiles - 1 - (int)blockIdx.x;              // tiles from the top: the kept rows first
             mbar_expect_tx(bar, BYTES);
-            const char *src = reinterpret_cast<const char *>(mid) + (size_t)blockIdx.x * BYTES;
-            for (int off = 0; off < BYTES; off += CH) tma_load_1d(k3_smem + off, src + off, CH, bar);
+            const char *src = reinterpret_cast<const char *>(mid) + (size_t)u0 * BYTES;
+            for (int off = 0; off < BYTES; off += CH)
+                tma_load_1d_policy(k3_smem + off, src + off, CH, bar, u0 >= keep_from_tile ? pol_normal : pol_stream);
         }
     }
     __syncthreads();
@@ -308,9 +370,15 @@ k3_pass2_r64(const float2 *__restrict__ mid, float2 *__restrict__ outp, const fl
     const float2 *rdB = buf + tid * 4 + c;                            // q = tid + 64 t  ->  tid + 65 t
     const float2 *twB = s_tw + tid;
     uint32_t phase = 0;
-    for (int u = blockIdx.x; u < n_tiles; u += gridDim.x) {
+    for (int tv = blockIdx.x; tv < n_tiles; tv += gridDim.x) {
+        const int u = n_tiles - 1 - tv;
         mbar_wait(bar, phase);
         phase ^= 1;
+        if (u >= keep_from_tile) {                                    // the tile has landed: its 1024 lines are dead in L2
+            const char *line = reinterpret_cast<const char *>(mid) + (size_t)u * BYTES + (size_t)threadIdx.x * 128;
+#pragma unroll
+            for (int i = 0; i < BYTES / 128 / 256; ++i) l2_discard_line(line + (size_t)i * 256 * 128);
+        }
         float2 v[64];
 #pragma unroll
         for (int t = 0; t < 64; ++t) v[t] = rdA[256 * t];
@@ -326,19 +394,21 @@ k3_pass2_r64(const float2 *__restrict__ mid, float2 *__restrict__ outp, const fl
         }
         __syncthreads();
         // the buffer is free: the next tile lands while this one is finished and stored from registers
-        const int nxt = u + gridDim.x;
+        const int nxt = tv + gridDim.x;
         if (threadIdx.x == 0 && nxt < n_tiles) {
+            const int nu = n_tiles - 1 - nxt;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(bar, BYTES);
-            const char *src = reinterpret_cast<const char *>(mid) + (size_t)nxt * BYTES;
-            for (int off = 0; off < BYTES; off += CH) tma_load_1d(k3_smem + off, src + off, CH, bar);
+            const char *src = reinterpret_cast<const char *>(mid) + (size_t)nu * BYTES;
+            for (int off = 0; off < BYTES; off += CH)
+                tma_load_1d_policy(k3_smem + off, src + off, CH, bar, nu >= keep_from_tile ? pol_normal : pol_stream);
         }
         Dft<64>::run(v);
         // X[k1 + N1 k2], k1 = 4 u + c, k2 = tid + 64 k: the 8 lanes x 4 rows of a warp write eight 32-byte runs
         float2 *dst = outp + 4 * (size_t)u + c + (size_t)tid * n1;
         const size_t step = 64 * n1;
 #pragma unroll
-        for (int k = 0; k < 64; ++k) { *dst = v[k]; dst += step; }
+        for (int k = 0; k < 64; ++k) { st_policy(dst, v[k], pol_stream); dst += step; }
     }
 }
 
@@ -487,20 +557,26 @@ template <class K> static int k3_grid(K kern, int threads, int smem, int tiles, 
     long long g = (long long)nb * sms;
     return (int)(g < tiles ? g : tiles);
 }
-template <int N1> static cudaError_t launch_pass1(int tiles, int sms, const CUtensorMap &a, float2 *mid, K3Tables tb,
-                                                  cudaStream_t st) {
+template <int N1, int KEEP> static cudaError_t launch_pass1k(int tiles, int sms, const CUtensorMap &a, float2 *mid,
+                                                             K3Tables tb, cudaStream_t st) {
     const int smem = N1 * 24 + 16;
-    cudaError_t e = cudaFuncSetAttribute(k3_pass1<N1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(k3_pass1<N1, KEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    k3_pass1<N1><<<k3_grid(k3_pass1<N1>, N1 / 8, smem, tiles, sms), N1 / 8, smem, st>>>(a, mid, tb, tiles);
+    k3_pass1<N1, KEEP><<<k3_grid(k3_pass1<N1, KEEP>, N1 / 8, smem, tiles, sms), N1 / 8, smem, st>>>(a, mid, tb, tiles);
     return cudaGetLastError();
 }
+template <int N1> static cudaError_t launch_pass1(int tiles, int sms, const CUtensorMap &a, float2 *mid, K3Tables tb,
+                                                  int keep, cudaStream_t st) {
+    if (keep == 2) return launch_pass1k<N1, 2>(tiles, sms, a, mid, tb, st);
+    if (keep == 1) return launch_pass1k<N1, 1>(tiles, sms, a, mid, tb, st);
+    return launch_pass1k<N1, 0>(tiles, sms, a, mid, tb, st);
+}
 template <int N2> static cudaError_t launch_pass2(int tiles, int sms, const float2 *mid, float2 *o, K3Tables tb,
-                                                  cudaStream_t st) {
+                                                  int keep_from_tile, cudaStream_t st) {
     const int smem = N2 * 40 + 16;
     cudaError_t e = cudaFuncSetAttribute(k3_pass2<N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    k3_pass2<N2><<<k3_grid(k3_pass2<N2>, N2 / 4, smem, tiles, sms), N2 / 4, smem, st>>>(mid, o, tb, tiles);
+    k3_pass2<N2><<<k3_grid(k3_pass2<N2>, N2 / 4, smem, tiles, sms), N2 / 4, smem, st>>>(mid, o, tb, tiles, keep_from_tile);
     return cudaGetLastError();
 }
 
@@ -546,20 +622,27 @@ extern "C" kopek_status kopek_fft_large_c2c_f32(const float *d_in, float *d_out,
         float2 *ptr; cudaStream_t s;
         ~Release() { cudaFreeAsync(ptr, s); }
     } release{mid, stream};
+    // L2 residency of the workspace: a `mid` of up to KOPEK_K3_KEEP_MB megabytes (default 72: n <= 2^23) is kept in
+    // L2 as a whole (pass 1 stores it evict_last, pass 2 reads it there and drops the lines); a larger one keeps its
+    // upper half of rows k1, which pass 2 reads first; 0 switches the keeping off (everything streams evict_first)
+    static const long keep_mb = getenv("KOPEK_K3_KEEP_MB") ? atol(getenv("KOPEK_K3_KEEP_MB")) : 72;
+    const int keep = keep_mb <= 0 ? 0 : n * sizeof(float2) <= ((uint64_t)keep_mb << 20) ? 2 : 1;
+    const int tiles2 = p.n1 / 4;
+    const int keep_from = (keep == 2 ? 0 : keep == 1 ? tiles2 / 2 : tiles2 + 1) * 4;     // in rows; the launches take tiles
     e = cudaErrorInvalidValue;
     switch (p.n1) {
-        case 256: e = launch_pass1<256>(p.n2 / 2, sms, in_map, mid, tb, stream); break;
-        case 512: e = launch_pass1<512>(p.n2 / 2, sms, in_map, mid, tb, stream); break;
-        case 1024: e = launch_pass1<1024>(p.n2 / 2, sms, in_map, mid, tb, stream); break;
-        case 2048: e = launch_pass1<2048>(p.n2 / 2, sms, in_map, mid, tb, stream); break;
-        case 4096: e = launch_pass1<4096>(p.n2 / 2, sms, in_map, mid, tb, stream); break;
+        case 256: e = launch_pass1<256>(p.n2 / 2, sms, in_map, mid, tb, keep, stream); break;
+        case 512: e = launch_pass1<512>(p.n2 / 2, sms, in_map, mid, tb, keep, stream); break;
+        case 1024: e = launch_pass1<1024>(p.n2 / 2, sms, in_map, mid, tb, keep, stream); break;
+        case 2048: e = launch_pass1<2048>(p.n2 / 2, sms, in_map, mid, tb, keep, stream); break;
+        case 4096: e = launch_pass1<4096>(p.n2 / 2, sms, in_map, mid, tb, keep, stream); break;
     }
     if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "four-step pass 1 (N1=%d): %s", p.n1, cudaGetErrorString(e));
     switch (p.n2) {
-        case 256: e = launch_pass2<256>(p.n1 / 4, sms, mid, reinterpret_cast<float2 *>(d_out), tb, stream); break;
-        case 512: e = launch_pass2<512>(p.n1 / 4, sms, mid, reinterpret_cast<float2 *>(d_out), tb, stream); break;
-        case 1024: e = launch_pass2<1024>(p.n1 / 4, sms, mid, reinterpret_cast<float2 *>(d_out), tb, stream); break;
-        case 2048: e = launch_pass2<2048>(p.n1 / 4, sms, mid, reinterpret_cast<float2 *>(d_out), tb, stream); break;
+        case 256: e = launch_pass2<256>(p.n1 / 4, sms, mid, reinterpret_cast<float2 *>(d_out), tb, keep_from / 4, stream); break;
+        case 512: e = launch_pass2<512>(p.n1 / 4, sms, mid, reinterpret_cast<float2 *>(d_out), tb, keep_from / 4, stream); break;
+        case 1024: e = launch_pass2<1024>(p.n1 / 4, sms, mid, reinterpret_cast<float2 *>(d_out), tb, keep_from / 4, stream); break;
+        case 2048: e = launch_pass2<2048>(p.n1 / 4, sms, mid, reinterpret_cast<float2 *>(d_out), tb, keep_from / 4, stream); break;
         case 4096: {
             static const bool r64 = !(getenv("KOPEK_K3_R64") && atoi(getenv("KOPEK_K3_R64")) == 0);   // tuning switch
             if (r64) {
@@ -567,11 +650,11 @@ extern "C" kopek_status kopek_fft_large_c2c_f32(const float *d_in, float *d_out,
                 e = cudaFuncSetAttribute(k3_pass2_r64, cudaFuncAttributeMaxDynamicSharedMemorySize, K3R_SMEM);
                 if (e == cudaSuccess) {
                     k3_pass2_r64<<<tiles < sms ? tiles : sms, 256, K3R_SMEM, stream>>>(mid, reinterpret_cast<float2 *>(d_out),
-                                                                                     p.tw2r, tiles);
+                                                                                     p.tw2r, tiles, keep_from / 4);
                     e = cudaGetLastError();
                 }
             } else {
-                e = launch_pass2<4096>(p.n1 / 4, sms, mid, reinterpret_cast<float2 *>(d_out), tb, stream);
+                e = launch_pass2<4096>(p.n1 / 4, sms, mid, reinterpret_cast<float2 *>(d_out), tb, keep_from / 4, stream);
             }
             break;
         }

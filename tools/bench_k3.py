@@ -1,5 +1,9 @@
 #!/usr/bin/env python3
-"""Time the four-step transform at 2^16 .. 2^24 (20 launches after 3 warm-ups) and check it against torch.fft."""
+"""K3 (four-step) timing and error against an f64 transform, 2^16 .. 2^24 points, with cuFFT C2C f32 beside it.
+
+    python tools/bench_k3.py [log2 sizes = 16,18,20,22,23,24]
+KOPEK_K3_KEEP_MB (read by the library) selects how much of the inter-pass workspace is asked to stay in L2.
+"""
 import os
 import sys
 
@@ -8,21 +12,33 @@ import torch  # noqa: E402
 
 from kopek_b200 import fft  # noqa: E402
 
+sizes = [int(v) for v in sys.argv[1].split(",")] if len(sys.argv) > 1 else [16, 18, 20, 22, 23, 24]
 st = torch.cuda.current_stream().cuda_stream
-for lg in [int(v) for v in sys.argv[1].split(",")] if len(sys.argv) > 1 else (16, 18, 20, 22, 24):
-    n = 1 << lg
-    a = torch.randn(n, dtype=torch.complex64, device="cuda")
-    b = torch.empty_like(a)
-    for _ in range(3):
-        fft.fft_large_device(a.data_ptr(), b.data_ptr(), n, 0, st)
+PEAK = 6535.1
+
+
+def timed(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(20):
-        fft.fft_large_device(a.data_ptr(), b.data_ptr(), n, 0, st)
+    for _ in range(iters):
+        fn()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 20
-    ref = torch.fft.fft(a.to(torch.complex128))
-    err = ((b.to(torch.complex128) - ref).abs().max() / ref.abs().max()).item()
-    print(f"2^{lg}: {ms:.4f} ms  {2 * n * 8 / ms / 1e6:7.1f} GB/s algorithmic  {100 * 2 * n * 8 / ms / 1e6 / 6535.1:5.1f}%  "
+    return e0.elapsed_time(e1) / iters
+
+
+print(f"KOPEK_K3_KEEP_MB={os.environ.get('KOPEK_K3_KEEP_MB', '(default)')} lib={os.environ.get('KOPEK_TUNE_TAG', 'production')}")
+for lg in sizes:
+    n = 1 << lg
+    a = torch.randn(n, dtype=torch.complex64, device="cuda")
+    a[12345 % n] += 100.0
+    b = torch.empty_like(a)
+    ms = timed(lambda: fft.fft_large_device(a.data_ptr(), b.data_ptr(), n, 0, st))
+    lib = timed(lambda: torch.fft.fft(a))
+    want = torch.fft.fft(a.to(torch.complex128))
+    err = ((b.to(torch.complex128) - want).abs().max() / want.abs().max()).item()
+    gbs = 2 * n * 8 / ms / 1e6
+    print(f"2^{lg}: {ms:.4f} ms  {gbs:7.1f} GB/s algorithmic {100 * gbs / PEAK:5.1f}%   cuFFT {lib:.4f} ms ({lib / ms:.2f}x)   "
           f"max rel err vs f64 {err:.2e}", flush=True)
