@@ -292,11 +292,18 @@ def parity_against_oracle(got, samples, n, hop, window, output):
     return res
 
 
-def block_checksums(torch, t):
-    """Two 64-bit checksums of a tensor's bits (order-sensitive): equal on both sides of a transfer <=> same bits."""
-    v = t.contiguous().view(torch.int32).to(torch.int64).reshape(-1)
-    idx = torch.arange(v.numel(), device=v.device, dtype=torch.int64)
-    return int(v.sum().item()), int((v * ((idx % 65521) + 1)).sum().item())
+def block_checksums(torch, t, piece: int = 1 << 26):
+    """Two 64-bit checksums of a tensor's bits (the second order-sensitive), accumulated piece by piece so that an
+    11 GB block costs 1.5 GB of temporaries: equal on both sides of a transfer <=> the same bits arrived."""
+    v = t.contiguous().view(torch.int32).reshape(-1)
+    a = b = 0
+    for off in range(0, v.numel(), piece):
+        w = v[off:off + piece].to(torch.int64)
+        idx = torch.arange(off, off + w.numel(), device=w.device, dtype=torch.int64)
+        a = (a + int(w.sum().item())) & 0xFFFFFFFFFFFFFFFF
+        b = (b + int((w * ((idx % 65521) + 1)).sum().item())) & 0xFFFFFFFFFFFFFFFF
+        del w, idx
+    return a, b
 
 
 # ----------------------------------------------------------------------------------------------- the bench ----
@@ -770,10 +777,18 @@ def bench_cfg4_gather(c, x4, frames4):
         local = torch.empty((frames4, bins), device=c.device, dtype=torch.float32)
         plan.exec_ptr(x4.data_ptr(), x4.numel(), local.data_ptr(), stream)
         torch.cuda.synchronize()
+    total = frames4 * c.world
+    # rank 0 needs the whole spectrogram beside its own shard: decide together whether it fits (never die of OOM here)
+    torch.cuda.empty_cache()
+    free = torch.cuda.mem_get_info()[0]
+    fits = [bool(free > total * bins * 4 + (6 << 30))]
+    dist.broadcast_object_list(fits, src=0)
+    if not fits[0]:
+        del local
+        return {"skipped": f"rank 0 has {free / 1e9:.0f} GB free, the gathered spectrogram needs {total * bins * 4 / 1e9:.0f} GB"}
     sums = block_checksums(torch, local)
     all_sums = [None] * c.world
     dist.all_gather_object(all_sums, sums)
-    total = frames4 * c.world
     # uneven frame_range would split differently: every rank holds exactly frames4 rows, so ranges are r * frames4
     full = None
     times = []
