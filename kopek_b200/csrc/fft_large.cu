@@ -187,6 +187,13 @@ __device__ __forceinline__ void tma_load_1d_policy(void *dst_smem, const void *s
 #endif
 }
 
+// Programmatic dependent launch: pass 2 is launched while pass 1 still runs; its CTAs become resident as pass-1 CTAs
+// retire, load their stage tables into shared memory and initialise their barrier, and only then wait for pass 1 to
+// have completed (griddepcontrol.wait) before the first read of `mid`.  Hides pass 2's prologue and launch latency
+// behind pass 1's tail: what a 2^20-point transform (two ~9 us kernels) spends a fifth of its time on.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 struct K3Tables {
     const float2 *tw_sub1;   // per-stage t-major twiddles of the N1-point sub-transform (k3_stage_twiddles)
     const float2 *tw_sub2;   // same for N2
@@ -242,6 +249,7 @@ k3_pass1(const __grid_constant__ CUtensorMap in_map, float2 *__restrict__ mid, K
     float2 *buf = reinterpret_cast<float2 *>(k3_smem);                 // N1 x 2 complex, dense
     float2 *s_tw = reinterpret_cast<float2 *>(k3_smem + (size_t)N1 * 16);   // stage twiddles, N1 entries
     uint64_t *bar = reinterpret_cast<uint64_t *>(k3_smem + (size_t)N1 * 24);
+    pdl_launch_dependents();                                  // pass 2 may start its prologue as SMs free up
     for (int i = threadIdx.x; i < N1; i += N1 / 8) s_tw[i] = tb.tw_sub1[i];
     const uint64_t pol_keep = l2_policy<2>(), pol_stream = l2_policy<1>();
     if (threadIdx.x == 0) {
@@ -303,6 +311,9 @@ k3_pass2(const float2 *__restrict__ mid, float2 *__restrict__ outp, K3Tables tb,
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    pdl_wait_primary();                                       // mid is complete and visible from here on
+    if (threadIdx.x == 0) {
         if ((int)blockIdx.x < n_tiles) {
             const int u0 = n_tiles - 1 - (int)blockIdx.x;
             mbar_expect_tx(bar, N2 * 32);
@@ -354,6 +365,9 @@ k3_pass2_r64(const float2 *__restrict__ mid, float2 *__restrict__ outp, const fl
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    pdl_wait_primary();                                       // mid is complete and visible from here on
+    if (threadIdx.x == 0) {
         if ((int)blockIdx.x < n_tiles) {
             const int u0 = n_tiles - 1 - (int)blockIdx.x;              // tiles from the top: the kept rows first
             mbar_expect_tx(bar, BYTES);
@@ -550,6 +564,23 @@ static kopek_status k3_get_plan(uint64_t n, int device, K3Plan *out) {
     return KOPEK_OK;
 }
 
+// launch with programmatic stream serialization: the kernel may begin before the previous one in the stream has
+// finished and must call griddepcontrol.wait before it touches that kernel's results (pdl_wait_primary above)
+template <class... P, class... A>
+static cudaError_t launch_pdl(void (*kern)(P...), int grid, int block, size_t smem, cudaStream_t st, A... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);
+}
+
 // persistent grid: as many CTAs as can be resident (occupancy x SMs), at most one per tile
 template <class K> static int k3_grid(K kern, int threads, int smem, int tiles, int sms) {
     int nb = 1;
@@ -576,8 +607,8 @@ template <int N2> static cudaError_t launch_pass2(int tiles, int sms, const floa
     const int smem = N2 * 40 + 16;
     cudaError_t e = cudaFuncSetAttribute(k3_pass2<N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    k3_pass2<N2><<<k3_grid(k3_pass2<N2>, N2 / 4, smem, tiles, sms), N2 / 4, smem, st>>>(mid, o, tb, tiles, keep_from_tile);
-    return cudaGetLastError();
+    return launch_pdl(k3_pass2<N2>, k3_grid(k3_pass2<N2>, N2 / 4, smem, tiles, sms), N2 / 4, (size_t)smem, st, mid, o, tb, tiles,
+                      keep_from_tile);
 }
 
 }  // namespace kopek
@@ -649,9 +680,8 @@ extern "C" kopek_status kopek_fft_large_c2c_f32(const float *d_in, float *d_out,
                 const int tiles = p.n1 / 4;
                 e = cudaFuncSetAttribute(k3_pass2_r64, cudaFuncAttributeMaxDynamicSharedMemorySize, K3R_SMEM);
                 if (e == cudaSuccess) {
-                    k3_pass2_r64<<<tiles < sms ? tiles : sms, 256, K3R_SMEM, stream>>>(mid, reinterpret_cast<float2 *>(d_out),
-                                                                                     p.tw2r, tiles, keep_from / 4);
-                    e = cudaGetLastError();
+                    e = launch_pdl(k3_pass2_r64, tiles < sms ? tiles : sms, 256, (size_t)K3R_SMEM, stream, (const float2 *)mid,
+                                   reinterpret_cast<float2 *>(d_out), (const float2 *)p.tw2r, tiles, keep_from / 4);
                 }
             } else {
                 e = launch_pass2<4096>(p.n1 / 4, sms, mid, reinterpret_cast<float2 *>(d_out), tb, keep_from / 4, stream);

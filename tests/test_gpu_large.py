@@ -59,3 +59,45 @@ def test_large_fft_argument_checks(built_lib):
         fft.fft_large_device(d.data_ptr(), o.data_ptr(), 1 << 15)          # too small
     with pytest.raises(KopekError):
         fft.fft_large_device(d.data_ptr(), o.data_ptr(), 100000)           # not a power of two
+
+
+def test_large_fft_same_length_on_two_streams(built_lib):
+    """Round-1 advice: two calls of the same length on different streams shared one pass-1 -> pass-2 workspace and
+    could overwrite each other's intermediate.  The workspace is now per call (stream-ordered pool): interleaved calls
+    on two streams, many times over, give exactly the bits of the calls made one after the other."""
+    import torch
+    from kopek_b200 import fft
+    n = 1 << 20
+    g = torch.Generator(device="cuda").manual_seed(3)
+    xs = [torch.randn(n, dtype=torch.complex64, device="cuda", generator=g) for _ in range(4)]
+    refs = []
+    st0 = torch.cuda.current_stream().cuda_stream
+    for x in xs:
+        o = torch.empty_like(x)
+        fft.fft_large_device(x.data_ptr(), o.data_ptr(), n, 0, st0)
+        torch.cuda.synchronize()
+        refs.append(o)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = [torch.zeros_like(x) for x in xs]
+    torch.cuda.synchronize()
+    for rep in range(25):
+        for i, x in enumerate(xs):
+            s = s1 if i % 2 == 0 else s2
+            fft.fft_large_device(x.data_ptr(), outs[i].data_ptr(), n, 0, s.cuda_stream)
+    torch.cuda.synchronize()
+    for o, r in zip(outs, refs):
+        assert torch.equal(o.view(torch.float32), r.view(torch.float32))
+
+
+def test_drop_in_many_lengths_keep_their_twiddle_tables(built_lib, oracle_mod):
+    """Round-1 advice: the twiddle tables of the f64 drop-in were an LRU of eight that freed the oldest table under
+    callers that might still launch on it.  They are kept for the life of the process now: twelve distinct lengths,
+    visited twice in different orders, stay bit-exact."""
+    from kopek_b200 import fft
+    rng = np.random.default_rng(12)
+    lengths = [2, 8, 16, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384]
+    xs = {n: rng.standard_normal(n) + 1j * rng.standard_normal(n) for n in lengths}
+    for order in (lengths, lengths[::-1], lengths[::2] + lengths[1::2]):
+        for n in order:
+            got = fft.fft(xs[n])
+            assert np.array_equal(got.view(np.uint64), oracle_mod.fft(xs[n]).view(np.uint64)), n
