@@ -44,6 +44,7 @@ template <int R> struct K1MGeom {
     static constexpr int EX_F2 = 16 * S;         // pass A -> B exchange
     static constexpr int ZX_F2 = 16 * S2;        // the finished Z, row k1 (S2 = T + 1 positions), column j'
     static constexpr size_t SMEM = sizeof(float2) * (EX_F2 + ZX_F2);
+    static constexpr size_t SMEM_WIN = sizeof(float2) * M;     // WINK == 3: the window table, N floats
 };
 
 // multiply by W256^m, m a compile-time index < 64 (the compile-time part of the split twiddle)
@@ -112,7 +113,10 @@ __device__ __forceinline__ float cs16_cos(int n1) {
 }
 __device__ __forceinline__ float cs16_sin(int n1) { return cs16_cos((n1 + 12) & 15); }
 
-// WINK: 0 = rectangular, 1 = window table in registers (any window; 32 registers), 2 = cosine-sum window
+// WINK: 0 = rectangular, 1 = window table in registers (any window; 32 registers), 3 = window table in SHARED memory
+// (any window: the team's CTA holds the N coefficients as [j][t] float4 = (w(2j, c = 0), w(2j, 1), w(2j + 1, 0),
+// w(2j + 1, 1)), so a lane reads its 32 coefficients with eight conflict-free 128-bit loads per frame and no window
+// register is held: custom windows keep 12 warps per SM), 2 = cosine-sum window
 // w[n] = a - b cos(2 pi n / N) (Hann, Hamming) evaluated on the fly: the samples of lane t sit at angles
 // theta_{t,c} + n1 pi/8 (n = 2 (T n1 + t) + c), so w/2 = a/2 + P_c cos(n1 pi/8) + Q_c sin(n1 pi/8) with the lane
 // constants P_c = -(b/2) cos theta, Q_c = (b/2) sin theta: 9 registers instead of 32, which is what lets three
@@ -130,6 +134,7 @@ k1m_kernel(const K1WParams p) {
     extern __shared__ __align__(16) unsigned char k1m_smem[];
     float2 *ex = reinterpret_cast<float2 *>(k1m_smem);
     float2 *zs = ex + G::EX_F2;                              // Z[k1 + 16 j'] at S2 k1 + j'
+    float4 *s_win = reinterpret_cast<float4 *>(zs + G::ZX_F2);   // WINK == 3 only: [j][t]
     const int t = threadIdx.x, k1 = t / R, r = t % R;
     float2 *exA = ex + t;                                    // + S k1'
     const float2 *exB = ex + S * k1 + r;                     // + R m
@@ -139,6 +144,15 @@ k1m_kernel(const K1WParams p) {
     const float2 *zB = zs + ((t & 15) ? S2 * (16 - (t & 15)) + (T - 1 - (t >> 4)) : T - (t >> 4));   // - R i
 
     const float2 *tab = reinterpret_cast<const float2 *>(p.tables);
+    if constexpr (WINK == 3) {
+        // (the exchange buffers hold 16 (T + R) + 16 (T + 1) float2, a multiple of two: s_win is 16-byte aligned)
+        for (int i = threadIdx.x; i < 8 * T; i += T) {
+            const int j = i / T, tt = i % T;
+            const float2 a = tab[T * (2 * j) + tt], b = tab[T * (2 * j + 1) + tt];
+            s_win[i] = make_float4(a.x, a.y, b.x, b.y);
+        }
+        if constexpr (T == 32) __syncwarp(); else __syncthreads();
+    }
     float2 rw[16], rp[16], tw[16], ph[R / 2];
     float2 cs0, cs1, cs_first, cs_last;
     float cs_a;
@@ -191,13 +205,23 @@ k1m_kernel(const K1WParams p) {
             if (pf_lane && fp < p.n_frames) prefetch_l2(p.x + fp * p.hop + 32 * t);
         }
         float2 e[16];
+        if constexpr (WINK == 3) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 w = s_win[T * j + t];
+                e[2 * j] = make_float2(vn[2 * j].x * w.x, vn[2 * j].y * w.y);
+                e[2 * j + 1] = make_float2(vn[2 * j + 1].x * w.z, vn[2 * j + 1].y * w.w);
+            }
+        }
         if constexpr (WINK == 2) {
             // the window values are loop invariant: without this the compiler hoists all 32 of them into registers
             asm volatile("" : "+f"(cs_a), "+f"(cs0.x), "+f"(cs0.y), "+f"(cs1.x), "+f"(cs1.y));
         }
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) {
-            if constexpr (WINK == 1) {
+            if constexpr (WINK == 3) {
+                // done above
+            } else if constexpr (WINK == 1) {
                 e[n1] = make_float2(vn[n1].x * rw[n1].x, vn[n1].y * rw[n1].y);
             } else if constexpr (WINK == 2) {
                 const float c = cs16_cos(n1), sn = cs16_sin(n1);

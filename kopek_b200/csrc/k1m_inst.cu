@@ -1,6 +1,7 @@
 // K1M instantiations (fft_team.cuh): team-per-frame kernels for N = 2048 (R = 4) and 4096 (R = 8).  Compiled once per
 // R (-DKOPEK_K1M_R=4 / 8, kopek_b200/build.py) so that the two sets of instantiations build in parallel; the host
 // tables and the dispatcher live in the R = 4 object.
+#include <atomic>
 #include <cmath>
 
 // Complex add / subtract as ONE packed instruction (add/sub.rn.f32x2 -> SASS FADD2) in this translation unit: the team
@@ -90,12 +91,24 @@ void k1m_build_tables(int n, const float *half_window, double cs_a, double cs_b,
 #endif
 template <int R, int WINK> struct K1MOcc {
     static constexpr int MINB = WINK == 1 ? 8 * 2 / R : KOPEK_K1M_WARPS * 2 / R;
+    static constexpr size_t SMEM = K1MGeom<R>::SMEM + (WINK == 3 ? K1MGeom<R>::SMEM_WIN : 0);
 };
 
 template <int R, int OUT, int WIN, bool FULL, bool VEC>
 static cudaError_t launch_m(const K1WParams &p, int grid, cudaStream_t stream, int *occ_out) {
     auto kern = k1m_kernel<R, OUT, WIN, K1MOcc<R, WIN>::MINB, KOPEK_K1M_PF, FULL, VEC>;
-    constexpr size_t smem = K1MGeom<R>::SMEM;
+    constexpr size_t smem = K1MOcc<R, WIN>::SMEM;
+    if constexpr (smem > 48 * 1024) {
+        // opt in to more than 48 KB of dynamic shared memory: once per instantiation and device (idempotent: a race is benign)
+        static std::atomic<bool> opted[64];
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !opted[dev].load(std::memory_order_acquire)) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < 64) opted[dev].store(true, std::memory_order_release);
+        }
+    }
     if (occ_out) {
         int nb = 0;
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, 16 * R, smem);
@@ -107,8 +120,7 @@ static cudaError_t launch_m(const K1WParams &p, int grid, cudaStream_t stream, i
 }
 
 // mode: 0 = HALF rows, 64-bit loads (every window kind); 1 = FULL rows; 2 = HALF rows, 32-bit loads; 3 = FULL rows,
-// 32-bit loads.  Modes 1..3 exist for the rectangular and cosine-sum windows (wink 0, 2); a custom window table with
-// FULL rows or unaligned frames runs on the generic kernel (kopek_cuda.cu).
+// 32-bit loads.  Modes 1..3 exist for every window kind but the register table (wink 1).
 template <int R, int OUT, int WIN>
 static cudaError_t launch_w(const K1WParams &p, int mode, int grid, cudaStream_t stream, int *occ_out) {
     if constexpr (WIN != 1) {
@@ -123,19 +135,23 @@ static cudaError_t launch_w(const K1WParams &p, int mode, int grid, cudaStream_t
 template <int R>
 static cudaError_t launch_r(const K1WParams &p, int output, int wink, int mode, int grid, cudaStream_t stream,
                             int *occ_out) {
-    switch (output * 3 + wink) {
+    switch (output * 4 + wink) {
         case 0: return launch_w<R, OUT_COMPLEX, 0>(p, mode, grid, stream, occ_out);
         case 1: return launch_w<R, OUT_COMPLEX, 1>(p, mode, grid, stream, occ_out);
         case 2: return launch_w<R, OUT_COMPLEX, 2>(p, mode, grid, stream, occ_out);
-        case 3: return launch_w<R, OUT_MAG, 0>(p, mode, grid, stream, occ_out);
-        case 4: return launch_w<R, OUT_MAG, 1>(p, mode, grid, stream, occ_out);
-        case 5: return launch_w<R, OUT_MAG, 2>(p, mode, grid, stream, occ_out);
-        case 6: return launch_w<R, OUT_POWER, 0>(p, mode, grid, stream, occ_out);
-        case 7: return launch_w<R, OUT_POWER, 1>(p, mode, grid, stream, occ_out);
-        case 8: return launch_w<R, OUT_POWER, 2>(p, mode, grid, stream, occ_out);
-        case 9: return launch_w<R, OUT_DB, 0>(p, mode, grid, stream, occ_out);
-        case 10: return launch_w<R, OUT_DB, 1>(p, mode, grid, stream, occ_out);
-        case 11: return launch_w<R, OUT_DB, 2>(p, mode, grid, stream, occ_out);
+        case 3: return launch_w<R, OUT_COMPLEX, 3>(p, mode, grid, stream, occ_out);
+        case 4: return launch_w<R, OUT_MAG, 0>(p, mode, grid, stream, occ_out);
+        case 5: return launch_w<R, OUT_MAG, 1>(p, mode, grid, stream, occ_out);
+        case 6: return launch_w<R, OUT_MAG, 2>(p, mode, grid, stream, occ_out);
+        case 7: return launch_w<R, OUT_MAG, 3>(p, mode, grid, stream, occ_out);
+        case 8: return launch_w<R, OUT_POWER, 0>(p, mode, grid, stream, occ_out);
+        case 9: return launch_w<R, OUT_POWER, 1>(p, mode, grid, stream, occ_out);
+        case 10: return launch_w<R, OUT_POWER, 2>(p, mode, grid, stream, occ_out);
+        case 11: return launch_w<R, OUT_POWER, 3>(p, mode, grid, stream, occ_out);
+        case 12: return launch_w<R, OUT_DB, 0>(p, mode, grid, stream, occ_out);
+        case 13: return launch_w<R, OUT_DB, 1>(p, mode, grid, stream, occ_out);
+        case 14: return launch_w<R, OUT_DB, 2>(p, mode, grid, stream, occ_out);
+        case 15: return launch_w<R, OUT_DB, 3>(p, mode, grid, stream, occ_out);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -144,7 +160,7 @@ static cudaError_t launch_r(const K1WParams &p, int output, int wink, int mode, 
 cudaError_t k1m_launch_r8(const K1WParams &p, int output, int wink, int mode, int grid, cudaStream_t stream, int *occ_out);
 cudaError_t k1m_launch(int n, const K1WParams &p, int output, int wink, int mode, int grid, cudaStream_t stream,
                        int *occ_out) {
-    if (wink < 0 || wink > 2 || mode < 0 || mode > 3) return cudaErrorInvalidValue;
+    if (wink < 0 || wink > 3 || mode < 0 || mode > 3) return cudaErrorInvalidValue;
     switch (n) {
         case 2048: return launch_r<4>(p, output, wink, mode, grid, stream, occ_out);
         case 4096: return k1m_launch_r8(p, output, wink, mode, grid, stream, occ_out);

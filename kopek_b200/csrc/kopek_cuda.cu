@@ -583,7 +583,10 @@ kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint
                 k1m_build_tables((int)n, nullptr, 0.0, 0.0, t.data());
                 K1WParams dummy{};
                 p->k1m_wink = window == KOPEK_WINDOW_RECT ? 0 : window == KOPEK_WINDOW_CUSTOM ? 1 : 2;
-                if (env && v == 301) p->k1m_wink = window == KOPEK_WINDOW_RECT ? 0 : 1;    // tuning: table window
+                if (env && v == 301) p->k1m_wink = window == KOPEK_WINDOW_RECT ? 0 : 1;    // tuning: register table
+                if (const char *wk = getenv("KOPEK_K1M_WINK"))                             // tuning: 1 / 2 / 3
+                    if (window != KOPEK_WINDOW_RECT && atoi(wk) >= 1 && atoi(wk) <= 3 &&
+                        !(atoi(wk) == 2 && window == KOPEK_WINDOW_CUSTOM)) p->k1m_wink = atoi(wk);
                 if ((e = cudaMalloc(&p->d_k1m, sizeof(float4) * t.size())) != cudaSuccess ||
                     (e = cudaMemcpy(p->d_k1m, t.data(), sizeof(float4) * t.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
                     (e = k1m_launch((int)n, dummy, (int)output, p->k1m_wink, 0, 0, nullptr,
