@@ -43,6 +43,9 @@ template <int R> struct K1MGeom {
     static constexpr int TABLE_F2 = WIN_F2 + RP_F2 + TW_F2 + PH_F2 + PW_F2 + CS_F2;
     static constexpr int EX_F2 = 16 * S;         // pass A -> B exchange
     static constexpr int ZX_F2 = 16 * S2;        // the finished Z, row k1 (S2 = T + 1 positions), column j'
+    // (The partner loads of the row-0 lanes put a third request on one bank pair: 16 extra wavefronts per warp and
+    // frame.  A shifted copy of row 0 in a 17th row removes them -- and was 2.5-3 points SLOWER, measured: the first
+    // warp, which writes the copy, becomes the straggler every other warp of the team waits for at the barrier.)
     static constexpr size_t SMEM = sizeof(float2) * (EX_F2 + ZX_F2);
     static constexpr size_t SMEM_WIN = sizeof(float2) * M;     // WINK == 3: the window table, N floats
 };
@@ -113,14 +116,15 @@ __device__ __forceinline__ float cs16_cos(int n1) {
 }
 __device__ __forceinline__ float cs16_sin(int n1) { return cs16_cos((n1 + 12) & 15); }
 
-// WINK: 0 = rectangular, 1 = window table in registers (any window; 32 registers), 3 = window table in SHARED memory
-// (any window: the team's CTA holds the N coefficients as [j][t] float4 = (w(2j, c = 0), w(2j, 1), w(2j + 1, 0),
-// w(2j + 1, 1)), so a lane reads its 32 coefficients with eight conflict-free 128-bit loads per frame and no window
-// register is held: custom windows keep 12 warps per SM), 2 = cosine-sum window
+// WINK: 0 = rectangular, 3 = window table in SHARED memory (any window, used for KOPEK_WINDOW_CUSTOM: the team's CTA
+// holds the N coefficients as [j][t] float4 = (w(2j, c = 0), w(2j, 1), w(2j + 1, 0), w(2j + 1, 1)), so a lane reads
+// its 32 coefficients with eight conflict-free 128-bit loads per frame and no window register is held; the round-1
+// form, 32 window registers and 8 warps per SM, was 4 / 1.3 points slower at 2048 / 4096 points and is gone),
+// 2 = cosine-sum window
 // w[n] = a - b cos(2 pi n / N) (Hann, Hamming) evaluated on the fly: the samples of lane t sit at angles
 // theta_{t,c} + n1 pi/8 (n = 2 (T n1 + t) + c), so w/2 = a/2 + P_c cos(n1 pi/8) + Q_c sin(n1 pi/8) with the lane
 // constants P_c = -(b/2) cos theta, Q_c = (b/2) sin theta: 9 registers instead of 32, which is what lets three
-// 128-lane teams (or six 64-lane teams) stay resident per SM.  The sum has an absolute error of ~3e-8, which is a
+// 128-lane teams (or six 64-lane teams) stay resident per SM, and it beats the shared-memory table by 3-4 points.  The sum has an absolute error of ~3e-8, which is a
 // large RELATIVE error where the window itself is ~1e-7 (the first and last samples of a frame), so the two edge
 // sixteenths (n1 = 0 and n1 = 15) keep their table values; everywhere else w/2 >= 0.019 and the error is < 2e-6.
 // FULL: all N bins per row (the conjugate mirror X[N - k] stored beside the computed half, see fft_warp1024b.cuh);
@@ -153,13 +157,9 @@ k1m_kernel(const K1WParams p) {
         }
         if constexpr (T == 32) __syncwarp(); else __syncthreads();
     }
-    float2 rw[16], rp[16], tw[16], ph[R / 2];
+    float2 rp[16], tw[16], ph[R / 2];
     float2 cs0, cs1, cs_first, cs_last;
     float cs_a;
-    if constexpr (WINK == 1) {
-#pragma unroll
-        for (int n1 = 0; n1 < 16; ++n1) rw[n1] = tab[T * n1 + t];
-    }
     if constexpr (WINK == 2) {
         const float2 *cs = tab + G::WIN_F2 + G::RP_F2 + G::TW_F2 + G::PH_F2 + G::PW_F2;
         cs0 = cs[t];
@@ -221,8 +221,6 @@ k1m_kernel(const K1WParams p) {
         for (int n1 = 0; n1 < 16; ++n1) {
             if constexpr (WINK == 3) {
                 // done above
-            } else if constexpr (WINK == 1) {
-                e[n1] = make_float2(vn[n1].x * rw[n1].x, vn[n1].y * rw[n1].y);
             } else if constexpr (WINK == 2) {
                 const float c = cs16_cos(n1), sn = cs16_sin(n1);
                 float w0, w1;

@@ -82,15 +82,14 @@ void k1m_build_tables(int n, const float *half_window, double cs_a, double cs_b,
 #ifndef KOPEK_K1M_PF
 #define KOPEK_K1M_PF 0      // L2 prefetch distance in frames per team: measured 0/2/3/5 -> no gain (not latency bound on HBM)
 #endif
-// resident teams per SM the register allocation is held to: 12 warps per SM (168 registers) for the rectangular and
-// cosine-sum windows -- measured 76 -> 86 % (N = 2048) and 70 -> 80 % (N = 4096) against 8 warps -- and 8 warps for
-// the table window, whose 32 extra registers would otherwise spill.  16 warps (-DKOPEK_K1M_WARPS=16: 128 registers,
+// resident teams per SM the register allocation is held to: 12 warps per SM (168 registers) -- measured 76 -> 86 %
+// (N = 2048) and 70 -> 80 % (N = 4096) against 8 warps.  16 warps (-DKOPEK_K1M_WARPS=16: 128 registers,
 // ~110 bytes of spills) is far worse: 84 -> 64 % (N = 2048) and 76 -> 57 % (N = 4096).
 #ifndef KOPEK_K1M_WARPS
 #define KOPEK_K1M_WARPS 12
 #endif
 template <int R, int WINK> struct K1MOcc {
-    static constexpr int MINB = WINK == 1 ? 8 * 2 / R : KOPEK_K1M_WARPS * 2 / R;
+    static constexpr int MINB = KOPEK_K1M_WARPS * 2 / R;
     static constexpr size_t SMEM = K1MGeom<R>::SMEM + (WINK == 3 ? K1MGeom<R>::SMEM_WIN : 0);
 };
 
@@ -119,16 +118,12 @@ static cudaError_t launch_m(const K1WParams &p, int grid, cudaStream_t stream, i
     return cudaGetLastError();
 }
 
-// mode: 0 = HALF rows, 64-bit loads (every window kind); 1 = FULL rows; 2 = HALF rows, 32-bit loads; 3 = FULL rows,
-// 32-bit loads.  Modes 1..3 exist for every window kind but the register table (wink 1).
+// mode: 0 = HALF rows, 64-bit loads; 1 = FULL rows; 2 = HALF rows, 32-bit loads; 3 = FULL rows, 32-bit loads
 template <int R, int OUT, int WIN>
 static cudaError_t launch_w(const K1WParams &p, int mode, int grid, cudaStream_t stream, int *occ_out) {
-    if constexpr (WIN != 1) {
-        if (mode == 1) return launch_m<R, OUT, WIN, true, true>(p, grid, stream, occ_out);
-        if (mode == 2) return launch_m<R, OUT, WIN, false, false>(p, grid, stream, occ_out);
-        if (mode == 3) return launch_m<R, OUT, WIN, true, false>(p, grid, stream, occ_out);
-    }
-    if (mode != 0) return cudaErrorInvalidValue;
+    if (mode == 1) return launch_m<R, OUT, WIN, true, true>(p, grid, stream, occ_out);
+    if (mode == 2) return launch_m<R, OUT, WIN, false, false>(p, grid, stream, occ_out);
+    if (mode == 3) return launch_m<R, OUT, WIN, true, false>(p, grid, stream, occ_out);
     return launch_m<R, OUT, WIN, false, true>(p, grid, stream, occ_out);
 }
 
@@ -137,19 +132,15 @@ static cudaError_t launch_r(const K1WParams &p, int output, int wink, int mode, 
                             int *occ_out) {
     switch (output * 4 + wink) {
         case 0: return launch_w<R, OUT_COMPLEX, 0>(p, mode, grid, stream, occ_out);
-        case 1: return launch_w<R, OUT_COMPLEX, 1>(p, mode, grid, stream, occ_out);
         case 2: return launch_w<R, OUT_COMPLEX, 2>(p, mode, grid, stream, occ_out);
         case 3: return launch_w<R, OUT_COMPLEX, 3>(p, mode, grid, stream, occ_out);
         case 4: return launch_w<R, OUT_MAG, 0>(p, mode, grid, stream, occ_out);
-        case 5: return launch_w<R, OUT_MAG, 1>(p, mode, grid, stream, occ_out);
         case 6: return launch_w<R, OUT_MAG, 2>(p, mode, grid, stream, occ_out);
         case 7: return launch_w<R, OUT_MAG, 3>(p, mode, grid, stream, occ_out);
         case 8: return launch_w<R, OUT_POWER, 0>(p, mode, grid, stream, occ_out);
-        case 9: return launch_w<R, OUT_POWER, 1>(p, mode, grid, stream, occ_out);
         case 10: return launch_w<R, OUT_POWER, 2>(p, mode, grid, stream, occ_out);
         case 11: return launch_w<R, OUT_POWER, 3>(p, mode, grid, stream, occ_out);
         case 12: return launch_w<R, OUT_DB, 0>(p, mode, grid, stream, occ_out);
-        case 13: return launch_w<R, OUT_DB, 1>(p, mode, grid, stream, occ_out);
         case 14: return launch_w<R, OUT_DB, 2>(p, mode, grid, stream, occ_out);
         case 15: return launch_w<R, OUT_DB, 3>(p, mode, grid, stream, occ_out);
         default: return cudaErrorInvalidValue;
@@ -160,7 +151,7 @@ static cudaError_t launch_r(const K1WParams &p, int output, int wink, int mode, 
 cudaError_t k1m_launch_r8(const K1WParams &p, int output, int wink, int mode, int grid, cudaStream_t stream, int *occ_out);
 cudaError_t k1m_launch(int n, const K1WParams &p, int output, int wink, int mode, int grid, cudaStream_t stream,
                        int *occ_out) {
-    if (wink < 0 || wink > 3 || mode < 0 || mode > 3) return cudaErrorInvalidValue;
+    if (wink < 0 || wink > 3 || wink == 1 || mode < 0 || mode > 3) return cudaErrorInvalidValue;
     switch (n) {
         case 2048: return launch_r<4>(p, output, wink, mode, grid, stream, occ_out);
         case 4096: return k1m_launch_r8(p, output, wink, mode, grid, stream, occ_out);

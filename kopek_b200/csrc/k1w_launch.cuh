@@ -28,11 +28,11 @@ cudaError_t k1w512_launch(const K1WParams &p, int output, bool win, int mode, in
 
 // team-per-frame kernels (fft_team.cuh): n = 2048 (64 lanes) / 4096 (128 lanes)
 int k1m_table_f4(int n);
-// wink: 0 rectangular, 1 window table in registers (half_window), 2 cosine-sum window w[n] = cs_a - cs_b cos(2 pi n / n)
-// on the fly, 3 window table in shared memory (half_window)
+// wink: 0 rectangular, 2 cosine-sum window w[n] = cs_a - cs_b cos(2 pi n / n) on the fly, 3 window table in shared
+// memory (half_window: custom windows)
 void k1m_build_tables(int n, const float *half_window, double cs_a, double cs_b, float4 *out /* k1m_table_f4(n) */);
 // mode: 0 HALF rows + 64-bit loads, 1 FULL rows, 2 HALF + 32-bit loads (odd hop / unaligned base), 3 FULL + 32-bit
-// loads; modes 1..3 for every wink but 1 (cudaErrorInvalidValue otherwise)
+// loads
 cudaError_t k1m_launch(int n, const K1WParams &p, int output, int wink, int mode, int grid, cudaStream_t stream,
                        int *occ_out /* teams per SM */);
 

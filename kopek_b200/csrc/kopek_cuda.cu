@@ -582,11 +582,9 @@ kopek_status kopek_plan_create(kopek_plan **plan, uint32_t n, uint32_t hop, uint
                 std::vector<float4> t(k1m_table_f4((int)n));
                 k1m_build_tables((int)n, nullptr, 0.0, 0.0, t.data());
                 K1WParams dummy{};
-                p->k1m_wink = window == KOPEK_WINDOW_RECT ? 0 : window == KOPEK_WINDOW_CUSTOM ? 1 : 2;
-                if (env && v == 301) p->k1m_wink = window == KOPEK_WINDOW_RECT ? 0 : 1;    // tuning: register table
-                if (const char *wk = getenv("KOPEK_K1M_WINK"))                             // tuning: 1 / 2 / 3
-                    if (window != KOPEK_WINDOW_RECT && atoi(wk) >= 1 && atoi(wk) <= 3 &&
-                        !(atoi(wk) == 2 && window == KOPEK_WINDOW_CUSTOM)) p->k1m_wink = atoi(wk);
+                p->k1m_wink = window == KOPEK_WINDOW_RECT ? 0 : window == KOPEK_WINDOW_CUSTOM ? 3 : 2;
+                if (const char *wk = getenv("KOPEK_K1M_WINK"))          // tuning: 3 = shared-memory table for Hann / Hamming too
+                    if (window != KOPEK_WINDOW_RECT && atoi(wk) == 3) p->k1m_wink = 3;
                 if ((e = cudaMalloc(&p->d_k1m, sizeof(float4) * t.size())) != cudaSuccess ||
                     (e = cudaMemcpy(p->d_k1m, t.data(), sizeof(float4) * t.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
                     (e = k1m_launch((int)n, dummy, (int)output, p->k1m_wink, 0, 0, nullptr,
@@ -686,11 +684,10 @@ static kopek_status stft_launch(const kopek_plan *plan, const float *d_samples, 
         return KOPEK_OK;
     }
     {
-        // team-per-frame kernels (2048 / 4096 points): HALF or FULL rows, any hop, any 4-byte aligned base; only a
-        // custom window table combined with FULL rows or unaligned frames is left to the generic kernel
+        // team-per-frame kernels (2048 / 4096 points): HALF or FULL rows, any hop, any 4-byte aligned base, any window
         const bool vec = plan->hop % 2 == 0 && (uintptr_t)d_samples % 8 == 0;
         const int mode = (plan->bins_mode == KOPEK_BINS_FULL ? 1 : 0) + (vec ? 0 : 2);
-        if (plan->d_k1m && (mode == 0 || plan->k1m_wink != 1)) {
+        if (plan->d_k1m) {
             K1WParams wp{};
             wp.x = d_samples;
             wp.out = d_out;

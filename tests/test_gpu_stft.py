@@ -374,3 +374,21 @@ def test_unaligned_frames_every_size(built_lib, oracle_mod, n, hop_kind, monkeyp
         gplan.exec_ptr(dx.data_ptr() + 4, (frames - 1) * hop + n, gen.data_ptr(), st)
         torch.cuda.synchronize()
     assert (np.abs(gen.cpu().numpy() - ref) / ref.max(axis=1, keepdims=True)).max() <= tol(n)
+
+
+@pytest.mark.parametrize("n", [2048, 4096])
+def test_custom_window_full_rows_and_odd_hop_on_the_team_kernels(built_lib, oracle_mod, n):
+    """Round 2: custom windows run from a shared-memory table in the team kernels, so they too get FULL rows and
+    unaligned frames (the last corner that fell back to the generic kernel)."""
+    from kopek_b200 import BINS_FULL, StftPlan, WINDOW_CUSTOM, signals
+    hop = n // 2 + 1
+    x = signals.white_noise(n + hop * 21, seed=n) + 0.25
+    w = np.blackman(n).astype(np.float32)
+    with StftPlan(n, hop, WINDOW_CUSTOM, 1, BINS_FULL, custom_window=w) as plan:
+        got = _run(plan, x)[:, :n]
+    frames = 1 + (x.size - n) // hop
+    ref = np.stack([np.abs(oracle_mod.fft((x[f * hop: f * hop + n] * w).astype(np.float32).astype(np.complex128)))
+                    for f in range(frames)])
+    assert got.shape == ref.shape
+    assert (np.abs(got - ref) / ref.max(axis=1, keepdims=True)).max() <= tol(n)
+    assert np.array_equal(got[:, 1:n // 2], got[:, :n // 2:-1])
