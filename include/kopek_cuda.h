@@ -61,7 +61,10 @@ enum {
 };
 #define KOPEK_BAND_ROW 10
 /* HALF: bins 0..n/2 (n/2+1 per frame, real input makes the rest redundant);
- * FULL: all n bins, as the reference's callers see them (graph/utils.rs:50 iterates all). */
+ * FULL: all n bins, as the reference's callers see them (graph/utils.rs:50 iterates all): bins n/2+1 .. n-1 are the
+ * conjugate mirror of a real frame, written by the same kernel beside the computed half.
+ * Every combination of n, hop (any value >= 1), window, output and bins, and any 4-byte aligned sample pointer, runs on
+ * the lane-group kernels; hops / bases that keep every frame 8-byte (n = 256: 16-byte) aligned take the vector loads. */
 enum { KOPEK_BINS_HALF = 0, KOPEK_BINS_FULL = 1 };
 
 /* Thread-local, NUL-terminated, valid until the next failing call on this thread. */
@@ -137,8 +140,9 @@ KOPEK_API kopek_status kopek_host_free(void *ptr);
 /* ---- 2b. live sliding window (examples/beep/view.rs:44,57-60,140-158) -----------------------
  * The beep view keeps the most recent 1024 samples in a VecDeque (new samples pushed at the back, old
  * ones popped at the front) and transforms the whole deque once per UI frame.  A kopek_stream is that
- * deque for the device (a ring in mapped pinned host memory which the kernel reads in place: one launch per
- * push, no DMA): push() appends `count` new host samples (history starts as zeros), then writes
+ * deque for the device (a host ring + a mapped pinned, aligned window which the kernel reads in place: one launch per
+ * push, no DMA, the same kernel whatever the push sizes add up to): push() appends `count` new host samples (history
+ * starts as zeros), then writes
  * the spectrum of the most recent n samples to h_out (kopek_stream_bins() elements, f32 or (re,im) f32).
  * input_scale multiplies every sample before the transform (1/32767 in beep/view.rs:143, 1 in pong). */
 typedef struct kopek_stream kopek_stream;
