@@ -138,3 +138,43 @@ pub fn stft_magnitude_multi(samples: &[f32], n: u32, hop: u32, hann: bool, devic
     }
     flat.chunks(bins).map(|r| r.to_vec()).collect()
 }
+
+/// The sliding window of the live examples (examples/beep/view.rs:44,57-60,140-158): the `VecDeque` of the most recent
+/// `n` samples lives in the library (kopek_stream_*); `push` appends the samples that arrived since the last UI frame
+/// and returns the magnitude spectrum (n/2 + 1 bins) of the window that ends at the newest one.  `input_scale` is the
+/// `/ 32767.0` of beep/view.rs:143 (1.0 in pong).
+pub struct LiveSpectrum {
+    raw: *mut sys::kopek_stream,
+    bins: usize,
+}
+unsafe impl Send for LiveSpectrum {}
+
+impl LiveSpectrum {
+    pub fn new(n: u32, hann: bool, input_scale: f32) -> LiveSpectrum {
+        let mut raw: *mut sys::kopek_stream = std::ptr::null_mut();
+        let window = if hann { sys::KOPEK_WINDOW_HANN } else { sys::KOPEK_WINDOW_RECT };
+        let st = unsafe { sys::kopek_stream_create(&mut raw, n, window, sys::KOPEK_OUT_MAG, input_scale, 0) };
+        if st != sys::KOPEK_OK {
+            panic!("kopek::fft::LiveSpectrum::new: {}", last_error());
+        }
+        let bins = unsafe { sys::kopek_stream_bins(raw) } as usize;
+        LiveSpectrum { raw, bins }
+    }
+
+    pub fn push(&mut self, new_samples: &[f32]) -> Vec<f32> {
+        let mut out = vec![0f32; self.bins];
+        let st = unsafe {
+            sys::kopek_stream_push(self.raw, new_samples.as_ptr(), new_samples.len() as u32, out.as_mut_ptr() as *mut _)
+        };
+        if st != sys::KOPEK_OK {
+            panic!("kopek::fft::LiveSpectrum::push: {}", last_error());
+        }
+        out
+    }
+}
+
+impl Drop for LiveSpectrum {
+    fn drop(&mut self) {
+        unsafe { sys::kopek_stream_destroy(self.raw) };
+    }
+}
