@@ -24,17 +24,23 @@ def _check(buf, n_elems):
     assert not bool((buf[GUARD:GUARD + n_elems] == SENT).any()), "kernel left output elements unwritten"
 
 
-@pytest.mark.parametrize("n,hop,window,output", [
-    (1024, 1024, 1, 1), (1024, 1024, 0, 3), (1024, 256, 1, 0), (1024, 1024, 0, 4), (1024, 1024, 1, 5),
-    (1024, 333, 1, 1), (256, 256, 0, 1), (512, 128, 1, 2), (2048, 512, 1, 3), (4096, 1024, 1, 1), (4096, 4096, 0, 0)])
-def test_stft_kernels_stay_in_bounds(built_lib, n, hop, window, output):
+@pytest.mark.parametrize("n,hop,window,output,bins", [
+    (1024, 1024, 1, 1, 0), (1024, 1024, 0, 3, 0), (1024, 256, 1, 0, 0), (1024, 1024, 0, 4, 0), (1024, 1024, 1, 5, 0),
+    (1024, 333, 1, 1, 0), (256, 256, 0, 1, 0), (512, 128, 1, 2, 0), (2048, 512, 1, 3, 0), (4096, 1024, 1, 1, 0),
+    (4096, 4096, 0, 0, 0),
+    # round 2: FULL rows (mirror stores) and 32-bit-load instantiations of every lane-group kernel
+    (1024, 1024, 1, 1, 1), (1024, 1023, 0, 0, 1), (256, 255, 1, 1, 1), (512, 512, 0, 3, 1), (512, 511, 1, 1, 0),
+    (2048, 2048, 1, 0, 1), (2048, 2047, 2, 1, 1), (4096, 4095, 1, 1, 1), (4096, 1026, 0, 2, 0), (1024, 1021, 1, 4, 0),
+    (2048, 512, 3, 1, 1), (4096, 4097, 3, 3, 0)])
+def test_stft_kernels_stay_in_bounds(built_lib, n, hop, window, output, bins):
     import torch
     from kopek_b200 import StftPlan
     frames = 1237                                     # not a multiple of frames-per-CTA or of the resident warps
     ns = (frames - 1) * hop + n
     xin, x = _guarded(ns, torch.float32)
     x.copy_(torch.randn(ns, device="cuda") + 2.0)     # strictly non-zero spectra so "unwritten" is detectable
-    with StftPlan(n, hop, window, output) as plan:
+    custom = np.hanning(n).astype(np.float32) + 0.1 if window == 3 else None
+    with StftPlan(n, hop, window, output, bins=bins, custom_window=custom) as plan:
         ne = frames * plan.pitch
         obuf, out = _guarded(ne, torch.complex64 if output == 0 else torch.float32)
         assert plan.exec_ptr(x.data_ptr(), ns, out.data_ptr(), torch.cuda.current_stream().cuda_stream) == frames
