@@ -33,18 +33,23 @@ def test_shard_ranges_match_the_python_mirror(built_lib):
             assert total == m.frames(ns)
 
 
-@pytest.mark.parametrize("n,hop,window,output,pitch", [(1024, 256, 1, 1, 0), (1024, 1024, 1, 1, 516), (2048, 512, 1, 3, 0),
-                                                       (256, 256, 0, 1, 0), (4096, 1024, 2, 2, 0), (1024, 512, 0, 0, 0)])
-def test_exec_host_is_bit_identical_to_one_device(built_lib, n, hop, window, output, pitch):
+@pytest.mark.parametrize("n,hop,window,output,pitch,bins", [
+    (1024, 256, 1, 1, 0, 0), (1024, 1024, 1, 1, 516, 0), (2048, 512, 1, 3, 0, 0), (256, 256, 0, 1, 0, 0),
+    (4096, 1024, 2, 2, 0, 0), (1024, 512, 0, 0, 0, 0),
+    (1024, 1001, 1, 1, 0, 1), (4096, 1023, 1, 1, 0, 1), (512, 77, 2, 0, 0, 1), (1024, 999, 1, 4, 0, 0)])
+def test_exec_host_is_bit_identical_to_one_device(built_lib, n, hop, window, output, pitch, bins):
+    """Shards start wherever floor(r F / R) * hop falls: with odd hops a device's sub-buffer is only 4-byte aligned, so
+    the same frame may take the 32-bit-load instantiation on one device count and the vector one on another -- the
+    two are bit-identical (tests/test_gpu_stft.py), and so is the sharded result."""
     import torch
 
     from kopek_b200 import StftPlan, signals
     from kopek_b200.sharded import MultiGpuStft
     devs = _devices(torch)
     x = signals.chirp(700_001, 48000.0, 20.0, 20000.0) + 0.01 * signals.white_noise(700_001, seed=n)
-    with StftPlan(n, hop, window, output, out_pitch=pitch, device=0) as plan:
+    with StftPlan(n, hop, window, output, bins=bins, out_pitch=pitch, device=0) as plan:
         ref = plan.exec_host(x)
-    with MultiGpuStft(devs, n, hop, window, output, out_pitch=pitch) as m:
+    with MultiGpuStft(devs, n, hop, window, output, bins=bins, out_pitch=pitch) as m:
         got = m.exec_host(x)
         assert got.shape == ref.shape and got.shape[0] == m.frames(x.size)
         assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
@@ -114,3 +119,21 @@ def test_mgpu_argument_errors(built_lib):
     bad = (C.c_int32 * 1)(99)
     assert lib.kopek_mgpu_create(C.byref(h), bad, 1, 1024, 1024, 0, 1, 0, 0) == _lib.ERR_INVALID      # no such device
     assert lib.kopek_mgpu_destroy(None) == _lib.OK
+
+
+def test_custom_window_on_every_device(built_lib):
+    """kopek_mgpu_set_custom_window uploads the coefficients to every device's plan."""
+    import torch
+
+    from kopek_b200 import StftPlan, WINDOW_CUSTOM, _lib, signals
+    from kopek_b200.sharded import MultiGpuStft
+    devs = _devices(torch)
+    n, hop = 2048, 700
+    w = np.kaiser(n, 6.0).astype(np.float32)
+    x = signals.white_noise(300_000, seed=5)
+    with StftPlan(n, hop, WINDOW_CUSTOM, 1, custom_window=w, device=0) as plan:
+        ref = plan.exec_host(x)
+    with MultiGpuStft(devs, n, hop, WINDOW_CUSTOM, 1) as m:
+        _lib.check(_lib.load().kopek_mgpu_set_custom_window(m._h, w.ctypes.data))
+        got = m.exec_host(x)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
