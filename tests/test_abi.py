@@ -100,3 +100,19 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in text and "from oracle" not in text and "ref_fft" not in text, f
                 assert "libkopek_oracle" not in text, f
+
+
+def test_c99_program_links_against_the_header_and_fails_loudly_without_a_gpu(built_lib, tmp_path):
+    """The boundary is a C ABI: a plain C99 translation unit includes the header, uses every kopek_mgpu_* entry point
+    and links with -lkopek_cuda.  In this container (no GPU) the first call must fail with the library's message."""
+    exe = str(tmp_path / "abi_check")
+    libdir = os.path.dirname(built_lib)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "abi_check.c"), "-L", libdir, "-lkopek_cuda",
+                    f"-Wl,-rpath,{libdir}", "-o", exe], check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    import torch
+    if torch.cuda.is_available() and torch.cuda.device_count() >= 2:
+        assert r.returncode == 0, r.stderr
+    else:
+        assert r.returncode == 1 and r.stderr.strip(), "a missing device must be an error with a message, not a fallback"
