@@ -179,6 +179,12 @@ KOPEK_API kopek_status kopek_synth_frames(float *d_out, uint64_t n_frames, uint3
  * Synchronous: returns after the count has been read back. */
 KOPEK_API kopek_status kopek_pcm16_to_f32(const int16_t *d_pcm, uint64_t n_frames, uint32_t channels, uint32_t channel,
                                           double divisor, float *d_out, int device, void *cuda_stream);
+/* kopek_pcm16_scale_f32: load_track_at_path of examples/graph/player.rs:81-102 -- the decoded Vec<[i16; 2]> becomes the
+ * interleaved f32 track [volume_factor * frame[0] as f32, volume_factor * frame[1] as f32, ...] (0.00002 there): one
+ * f32 product per value, bit-exact.  n_values = frames * channels; d_pcm 2-byte, d_out 4-byte aligned (16-byte
+ * aligned buffers take the 128-bit path); asynchronous on cuda_stream. */
+KOPEK_API kopek_status kopek_pcm16_scale_f32(const int16_t *d_pcm, uint64_t n_values, float factor, float *d_out, int device,
+                                             void *cuda_stream);
 KOPEK_API kopek_status kopek_detect_bpm(const int16_t *d_frames, uint64_t n_frames, float sample_rate, uint32_t *bpm_out,
                                         uint32_t *beats_out, float *d_block_e, float *d_avg_e, int device,
                                         void *cuda_stream);

@@ -2,6 +2,8 @@
 // (src/decoder.rs:1-31: Vec<[i16; 2]>):
 //   kopek_pcm16_to_f32  -- the marshalling of examples/graph/player.rs:56-59 (frame[0] as f64 / i16::MAX) into the f32
 //                          sample buffer the STFT plans transform; bit-exact (f64 division, one narrowing)
+//   kopek_pcm16_scale_f32 -- the marshalling of examples/graph/player.rs:81-102 (load_track_at_path): every i16 value of
+//                          the decoded frames, channels interleaved, becomes volume_factor * (value as f32); bit-exact
 //   kopek_detect_bpm    -- the energy pass of detect_bpm (src/decoder.rs:39-71); bit-exact: the per-frame terms are
 //                          computed in parallel (no contraction), and every f32 sum of the reference -- a sequential
 //                          left fold -- is added in the reference's order by ONE thread per 1024-frame block (43 per
@@ -35,6 +37,31 @@ __global__ void __launch_bounds__(256) pcm16x2_to_f32_kernel(const int4 *__restr
         }
         out[i] = make_float4(r[0], r[1], r[2], r[3]);
     }
+}
+
+// load_track_at_path (examples/graph/player.rs:87-97): [volume_factor * frame[0] as f32, volume_factor * frame[1] as f32]
+// flattened -- one f32 product per i16 value.  Eight values per thread: one 128-bit load, two 128-bit stores.
+__global__ void __launch_bounds__(256) pcm16_scale_f32_kernel(const int4 *__restrict__ pcm, uint64_t n_octets, float factor,
+                                                              float4 *__restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_octets; i += stride) {
+        const int4 v = __ldg(pcm + i);
+        const int w[4] = {v.x, v.y, v.z, v.w};
+        float r[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            r[2 * k] = __fmul_rn(factor, (float)(short)(w[k] & 0xffff));
+            r[2 * k + 1] = __fmul_rn(factor, (float)(w[k] >> 16));
+        }
+        out[2 * i] = make_float4(r[0], r[1], r[2], r[3]);
+        out[2 * i + 1] = make_float4(r[4], r[5], r[6], r[7]);
+    }
+}
+__global__ void __launch_bounds__(256) pcm16_scale_f32_tail_kernel(const int16_t *__restrict__ pcm, uint64_t n, float factor,
+                                                                   float *__restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = __fmul_rn(factor, (float)pcm[i]);
 }
 
 // f[0].powf(2.0) + f[1].powf(2.0) of one frame (src/decoder.rs:52,61), f = s as f32 / i16::MAX as f32
@@ -156,6 +183,33 @@ extern "C" kopek_status kopek_pcm16_to_f32(const int16_t *d_pcm, uint64_t n_fram
         const uint64_t rest = n_frames - done;
         const unsigned grid = (unsigned)std::min<uint64_t>((rest + 255) / 256, (uint64_t)sms * 8);
         pcm16_to_f32_kernel<<<grid, 256, 0, st>>>(d_pcm + done * channels, rest, channels, channel, divisor, d_out + done);
+    }
+    KOPEK_CUDA(cudaGetLastError());
+    return KOPEK_OK;
+}
+
+extern "C" kopek_status kopek_pcm16_scale_f32(const int16_t *d_pcm, uint64_t n_values, float factor, float *d_out, int device,
+                                              void *cuda_stream) {
+    if (n_values == 0) return KOPEK_OK;
+    if (!d_pcm || !d_out) return fail(KOPEK_ERR_INVALID, "NULL device pointer");
+    if ((uintptr_t)d_pcm % 2 || (uintptr_t)d_out % 4) return fail(KOPEK_ERR_INVALID, "misaligned device pointer");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(KOPEK_ERR_CUDA, "cannot select device %d", device);
+    int sms = 0;
+    KOPEK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    uint64_t done = 0;
+    if ((uintptr_t)d_pcm % 16 == 0 && (uintptr_t)d_out % 16 == 0 && n_values >= 8) {
+        const uint64_t octets = n_values / 8;
+        const unsigned grid = (unsigned)std::min<uint64_t>((octets + 255) / 256, (uint64_t)sms * 8);
+        pcm16_scale_f32_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const int4 *>(d_pcm), octets, factor,
+                                                     reinterpret_cast<float4 *>(d_out));
+        done = octets * 8;
+    }
+    if (done < n_values) {
+        const uint64_t rest = n_values - done;
+        const unsigned grid = (unsigned)std::min<uint64_t>((rest + 255) / 256, (uint64_t)sms * 8);
+        pcm16_scale_f32_tail_kernel<<<grid, 256, 0, st>>>(d_pcm + done, rest, factor, d_out + done);
     }
     KOPEK_CUDA(cudaGetLastError());
     return KOPEK_OK;

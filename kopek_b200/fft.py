@@ -84,6 +84,11 @@ def pcm16_to_f32_device(d_pcm: int, n_frames: int, d_out: int, channels: int = 2
     check(_lib.load().kopek_pcm16_to_f32(d_pcm, n_frames, channels, channel, divisor, d_out, device, stream or None))
 
 
+def pcm16_scale_f32_device(d_pcm: int, n_values: int, factor: float, d_out: int, device: int = 0, stream: int = 0) -> None:
+    """kopek_pcm16_scale_f32: volume_factor * (value as f32) over interleaved i16 values (examples/graph/player.rs:81-102)."""
+    check(_lib.load().kopek_pcm16_scale_f32(d_pcm, n_values, factor, d_out, device, stream or None))
+
+
 def detect_bpm_device(d_frames: int, n_frames: int, sample_rate: float = 44100.0, d_block_e: int = 0, d_avg_e: int = 0,
                       device: int = 0, stream: int = 0):
     """kopek_detect_bpm: kopek::decoder::detect_bpm (src/decoder.rs:39-71) on device-resident [n][2] i16 frames.

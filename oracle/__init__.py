@@ -62,6 +62,7 @@ def lib() -> C.CDLL:
         L.oracle_stft_mag.argtypes = [vp, sz, sz, sz, i32, sz, i32, i32, vp]
         L.oracle_max_threads.restype = i32
         L.oracle_pcm16_to_f32.argtypes = [vp, sz, sz, sz, f64, vp]
+        L.oracle_pcm16_scale_f32.argtypes = [vp, sz, f32, vp]
         L.oracle_detect_bpm.restype = C.c_int64
         L.oracle_detect_bpm.argtypes = [vp, sz, f32, vp, vp, vp]
         _lib = L
@@ -205,6 +206,14 @@ def pcm16_to_f32(pcm, channel: int = 0, divisor: float = 32767.0) -> np.ndarray:
         pcm = pcm[:, None]
     out = np.empty(pcm.shape[0], dtype=np.float32)
     lib().oracle_pcm16_to_f32(_p(pcm), pcm.shape[0], pcm.shape[1], channel, divisor, _p(out))
+    return out
+
+
+def pcm16_scale_f32(pcm, factor: float = 0.00002) -> np.ndarray:
+    """examples/graph/player.rs:81-102 (load_track_at_path): volume_factor * (value as f32), channels interleaved."""
+    pcm = np.ascontiguousarray(pcm, dtype=np.int16).reshape(-1)
+    out = np.empty(pcm.size, dtype=np.float32)
+    lib().oracle_pcm16_scale_f32(_p(pcm), pcm.size, factor, _p(out))
     return out
 
 

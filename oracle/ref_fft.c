@@ -397,6 +397,12 @@ ORACLE_API void oracle_pcm16_to_f32(const int16_t *pcm, size_t n_frames, size_t 
     for (size_t i = 0; i < n_frames; ++i) out[i] = (float)((double)pcm[i * channels + channel] / divisor);
 }
 
+/* load_track_at_path, examples/graph/player.rs:81-102: frames.iter().map(|frame| [volume_factor * frame[0] as f32,
+ * volume_factor * frame[1] as f32]).flatten() -- one f32 product per i16 value (volume_factor = 0.00002 there). */
+ORACLE_API void oracle_pcm16_scale_f32(const int16_t *pcm, size_t n_values, float factor, float *out) {
+    for (size_t i = 0; i < n_values; ++i) out[i] = factor * (float)pcm[i];
+}
+
 /* detect_bpm, src/decoder.rs:39-71, statement by statement.
  *   f_frames = frames.map(|f| [f[0] as f32 / i16::MAX as f32, f[1] as f32 / i16::MAX as f32])     :41-44
  *   duration = (frames.len() as f32 / sample_rate) as usize                                        :46 (:35-37)

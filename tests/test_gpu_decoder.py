@@ -124,3 +124,27 @@ def test_pcm16_frames_straight_into_the_plan(built_lib, oracle_mod, n, hop, outp
             if output == 1:
                 ref = oracle_mod.stft_mag(oracle_mod.pcm16_to_f32(x, channel), n, hop, window)
                 assert (np.abs(a.cpu().numpy() - ref) / ref.max(axis=1, keepdims=True)).max() <= tol(n)
+
+
+def test_pcm16_scale_f32_is_bit_exact(built_lib, oracle_mod):
+    """load_track_at_path (examples/graph/player.rs:81-102): volume_factor * (value as f32) over the interleaved frames;
+    every i16 value, aligned and unaligned buffers, lengths that leave a tail, the 128-bit path and the scalar one."""
+    import torch
+    from kopek_b200 import fft
+    allv = np.arange(-32768, 32768, dtype=np.int16)                       # every possible value once
+    rng = np.random.default_rng(9)
+    for pcm, offset in ((allv, 0), (rng.integers(-32768, 32768, size=200_003, dtype=np.int16), 0),
+                        (rng.integers(-32768, 32768, size=4099, dtype=np.int16), 1), (allv[:5], 0)):
+        d = torch.from_numpy(pcm).cuda()
+        n = pcm.size - offset
+        for factor in (0.00002, 1.0 / 32767.0, -3.5):
+            out = torch.full((n + 8,), float("nan"), device="cuda")
+            fft.pcm16_scale_f32_device(d.data_ptr() + 2 * offset, n, factor, out.data_ptr())
+            torch.cuda.synchronize()
+            got = out.cpu().numpy()
+            want = oracle_mod.pcm16_scale_f32(pcm[offset:], factor)
+            assert np.array_equal(got[:n].view(np.uint32), want.view(np.uint32)), (pcm.size, offset, factor)
+            assert np.isnan(got[n:]).all()
+    # the numpy statement of the same expression (f32 product) agrees with the oracle
+    want = np.float32(0.00002) * allv.astype(np.float32)
+    assert np.array_equal(oracle_mod.pcm16_scale_f32(allv, 0.00002).view(np.uint32), want.view(np.uint32))

@@ -240,3 +240,11 @@ def test_pcm16_marshalling(oracle_mod):
     q1 = (e.astype(np.float64) * np.float64(r) + q0.astype(np.float64)).astype(np.float32)
     np.testing.assert_array_equal(q1, ref)
     np.testing.assert_array_equal((sf / np.float32(32767.0)).astype(np.float32), ref)
+
+
+def test_load_track_scaling(oracle_mod):
+    """examples/graph/player.rs:81-102: volume_factor * frame[c] as f32, flattened -- an f32 product per value."""
+    allv = np.arange(-32768, 32768, dtype=np.int16)
+    got = oracle_mod.pcm16_scale_f32(allv, 0.00002)
+    assert np.array_equal(got.view(np.uint32), (np.float32(0.00002) * allv.astype(np.float32)).view(np.uint32))
+    assert got[32768] == 0.0 and got[-1] == np.float32(0.00002) * np.float32(32767)

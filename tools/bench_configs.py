@@ -111,6 +111,8 @@ pcm = torch.randint(-32768, 32767, (nfr, 2), dtype=torch.int16, device="cuda")
 o32 = torch.empty(nfr, device="cuda")
 ms = timed(lambda: fft.pcm16_to_f32_device(pcm.data_ptr(), nfr, o32.data_ptr(), 2, 0, stream=st), iters=10)
 dec_rows.append((f"pcm16 -> f32, channel 0 / 32767 (f64 division), 2^28 stereo frames", ms, nfr * 8))
+ms = timed(lambda: fft.pcm16_scale_f32_device(pcm.data_ptr(), nfr, 0.00002, o32.data_ptr(), stream=st), iters=10)
+dec_rows.append((f"pcm16 -> f32 track, 0.00002 * value (load_track_at_path), 2^28 values", ms, nfr * 6))
 del o32
 pl = StftPlan(1024, 1024, WINDOW_HANN, OUT_MAG)
 fr = nfr // 1024
