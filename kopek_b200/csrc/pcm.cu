@@ -41,20 +41,29 @@ __global__ void __launch_bounds__(256) pcm16x2_to_f32_kernel(const int4 *__restr
 
 // load_track_at_path (examples/graph/player.rs:87-97): [volume_factor * frame[0] as f32, volume_factor * frame[1] as f32]
 // flattened -- one f32 product per i16 value.  Eight values per thread: one 128-bit load, two 128-bit stores.
+__device__ __forceinline__ void pcm16_scale_octet(const int4 v, float factor, float4 *out) {
+    const int w[4] = {v.x, v.y, v.z, v.w};
+    float r[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        r[2 * k] = __fmul_rn(factor, (float)(short)(w[k] & 0xffff));
+        r[2 * k + 1] = __fmul_rn(factor, (float)(w[k] >> 16));
+    }
+    __stcs(out, make_float4(r[0], r[1], r[2], r[3]));          // the track is written once and not read back here
+    __stcs(out + 1, make_float4(r[4], r[5], r[6], r[7]));
+}
 __global__ void __launch_bounds__(256) pcm16_scale_f32_kernel(const int4 *__restrict__ pcm, uint64_t n_octets, float factor,
                                                               float4 *__restrict__ out) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_octets; i += stride) {
-        const int4 v = __ldg(pcm + i);
-        const int w[4] = {v.x, v.y, v.z, v.w};
-        float r[8];
+    // four independent 128-bit loads in flight per thread and iteration (a warp covers 4 x 512 contiguous bytes)
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 4;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x * 4 + threadIdx.x; i0 < n_octets; i0 += stride) {
+        int4 v[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            r[2 * k] = __fmul_rn(factor, (float)(short)(w[k] & 0xffff));
-            r[2 * k + 1] = __fmul_rn(factor, (float)(w[k] >> 16));
-        }
-        out[2 * i] = make_float4(r[0], r[1], r[2], r[3]);
-        out[2 * i + 1] = make_float4(r[4], r[5], r[6], r[7]);
+        for (int u = 0; u < 4; ++u)
+            if (i0 + u * 256 < n_octets) v[u] = __ldcs(pcm + i0 + u * 256);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i0 + u * 256 < n_octets) pcm16_scale_octet(v[u], factor, out + 2 * (i0 + u * 256));
     }
 }
 __global__ void __launch_bounds__(256) pcm16_scale_f32_tail_kernel(const int16_t *__restrict__ pcm, uint64_t n, float factor,
@@ -201,7 +210,7 @@ extern "C" kopek_status kopek_pcm16_scale_f32(const int16_t *d_pcm, uint64_t n_v
     uint64_t done = 0;
     if ((uintptr_t)d_pcm % 16 == 0 && (uintptr_t)d_out % 16 == 0 && n_values >= 8) {
         const uint64_t octets = n_values / 8;
-        const unsigned grid = (unsigned)std::min<uint64_t>((octets + 255) / 256, (uint64_t)sms * 8);
+        const unsigned grid = (unsigned)std::min<uint64_t>((octets + 1023) / 1024, (uint64_t)sms * 8);
         pcm16_scale_f32_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const int4 *>(d_pcm), octets, factor,
                                                      reinterpret_cast<float4 *>(d_out));
         done = octets * 8;
