@@ -392,3 +392,23 @@ def test_custom_window_full_rows_and_odd_hop_on_the_team_kernels(built_lib, orac
     assert got.shape == ref.shape
     assert (np.abs(got - ref) / ref.max(axis=1, keepdims=True)).max() <= tol(n)
     assert np.array_equal(got[:, 1:n // 2], got[:, :n // 2:-1])
+
+
+@pytest.mark.parametrize("n_in,n", [(441, 512), (1000, 1024), (480, 512), (3000, 4096)])
+def test_zero_padded_callback_frames_through_a_custom_window(built_lib, oracle_mod, n_in, n):
+    """The graph example hands fft() whatever length the audio callback delivered (examples/graph/player.rs:48-61), and
+    fft() pads it with zeros to the next power of two (src/fft.rs:31-36).  Many such frames at once: hop = n_in, frame
+    size n, and a custom window that is 1 on [0, n_in) and 0 on the tail -- the tail samples (the next frame's) are
+    multiplied by zero, which IS the zero padding.  Checked against fft() of every padded frame."""
+    from kopek_b200 import StftPlan, WINDOW_CUSTOM, signals
+    frames = 29
+    x = signals.chirp(frames * n_in + (n - n_in), 44100.0, 100.0, 9000.0)
+    w = np.zeros(n, dtype=np.float32)
+    w[:n_in] = 1.0
+    with StftPlan(n, n_in, WINDOW_CUSTOM, 1, custom_window=w) as plan:
+        got = _run(plan, x)[:, :plan.bins]
+    assert got.shape == (frames, n // 2 + 1)
+    ref = np.stack([oracle_mod.mag_norm(oracle_mod.fft(oracle_mod.marshal(x[f * n_in:(f + 1) * n_in])))[: n // 2 + 1]
+                    for f in range(frames)])
+    assert (np.abs(got - ref) / ref.max(axis=1, keepdims=True)).max() <= tol(n)
+    assert np.array_equal(got.argmax(axis=1), ref.argmax(axis=1))
