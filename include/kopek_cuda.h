@@ -185,6 +185,11 @@ KOPEK_API kopek_status kopek_pcm16_to_f32(const int16_t *d_pcm, uint64_t n_frame
  * aligned buffers take the 128-bit path); asynchronous on cuda_stream. */
 KOPEK_API kopek_status kopek_pcm16_scale_f32(const int16_t *d_pcm, uint64_t n_values, float factor, float *d_out, int device,
                                              void *cuda_stream);
+/* kopek_f32_downmix: the capture callback of examples/pong/audio.rs:57-70 -- every interleaved f32 frame of `channels`
+ * samples becomes ONE sample: the first two channels summed from 0.0 in order, divided by the channel count (what the
+ * game then pops 1024 of and hands to fft(), examples/pong/main.rs:175-196).  Bit-exact; asynchronous on cuda_stream. */
+KOPEK_API kopek_status kopek_f32_downmix(const float *d_frames, uint64_t n_frames, uint32_t channels, float *d_out, int device,
+                                         void *cuda_stream);
 KOPEK_API kopek_status kopek_detect_bpm(const int16_t *d_frames, uint64_t n_frames, float sample_rate, uint32_t *bpm_out,
                                         uint32_t *beats_out, float *d_block_e, float *d_avg_e, int device,
                                         void *cuda_stream);

@@ -54,6 +54,7 @@ SYMBOLS = {
                                   C.c_float, _u64, _u64, C.c_int, _vp]),
     "kopek_pcm16_to_f32": (_i32, [_vp, _u64, _u32, _u32, C.c_double, _vp, C.c_int, _vp]),
     "kopek_pcm16_scale_f32": (_i32, [_vp, _u64, C.c_float, _vp, C.c_int, _vp]),
+    "kopek_f32_downmix": (_i32, [_vp, _u64, _u32, _vp, C.c_int, _vp]),
     "kopek_detect_bpm": (_i32, [_vp, _u64, C.c_float, C.POINTER(_u32), C.POINTER(_u32), _vp, _vp, C.c_int, _vp]),
     "kopek_detect_bpm_host": (_i32, [_vp, _u64, C.c_float, C.POINTER(_u32), C.POINTER(_u32), C.c_int]),
     "kopek_device_alloc": (_i32, [C.POINTER(_vp), _sz, C.c_int]),

@@ -4,6 +4,8 @@
 //                          sample buffer the STFT plans transform; bit-exact (f64 division, one narrowing)
 //   kopek_pcm16_scale_f32 -- the marshalling of examples/graph/player.rs:81-102 (load_track_at_path): every i16 value of
 //                          the decoded frames, channels interleaved, becomes volume_factor * (value as f32); bit-exact
+//   kopek_f32_downmix   -- the capture callback of examples/pong/audio.rs:57-70: every interleaved f32 frame becomes
+//                          ((0.0 + f[0]) + f[1]) / channels (the first TWO channels summed, divided by ALL); bit-exact
 //   kopek_detect_bpm    -- the energy pass of detect_bpm (src/decoder.rs:39-71); bit-exact: the per-frame terms are
 //                          computed in parallel (no contraction), and every f32 sum of the reference -- a sequential
 //                          left fold -- is added in the reference's order by ONE thread per 1024-frame block (43 per
@@ -71,6 +73,28 @@ __global__ void __launch_bounds__(256) pcm16_scale_f32_tail_kernel(const int16_t
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         out[i] = __fmul_rn(factor, (float)pcm[i]);
+}
+
+// examples/pong/audio.rs:60-66: average = 0.0; for sample in frame.iter().take(2) { average += sample }; average /= len
+// (0.0 + x is x except that it turns -0.0 into +0.0: kept).  Stereo: one 64-bit load per frame.
+__global__ void __launch_bounds__(256) f32_downmix_kernel(const float *__restrict__ frames, uint64_t n_frames, uint32_t channels,
+                                                          float *__restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const float len = (float)channels;
+    const bool vec2 = channels == 2 && ((uintptr_t)frames % 8) == 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_frames; i += stride) {
+        float a, b = 0.0f;
+        if (vec2) {
+            const float2 f = __ldcs(reinterpret_cast<const float2 *>(frames) + i);
+            a = f.x, b = f.y;
+        } else {
+            a = __ldg(frames + i * channels);
+            if (channels > 1) b = __ldg(frames + i * channels + 1);
+        }
+        float avg = __fadd_rn(0.0f, a);
+        if (channels > 1) avg = __fadd_rn(avg, b);
+        out[i] = __fdiv_rn(avg, len);
+    }
 }
 
 // f[0].powf(2.0) + f[1].powf(2.0) of one frame (src/decoder.rs:52,61), f = s as f32 / i16::MAX as f32
@@ -220,6 +244,22 @@ extern "C" kopek_status kopek_pcm16_scale_f32(const int16_t *d_pcm, uint64_t n_v
         const unsigned grid = (unsigned)std::min<uint64_t>((rest + 255) / 256, (uint64_t)sms * 8);
         pcm16_scale_f32_tail_kernel<<<grid, 256, 0, st>>>(d_pcm + done, rest, factor, d_out + done);
     }
+    KOPEK_CUDA(cudaGetLastError());
+    return KOPEK_OK;
+}
+
+extern "C" kopek_status kopek_f32_downmix(const float *d_frames, uint64_t n_frames, uint32_t channels, float *d_out, int device,
+                                          void *cuda_stream) {
+    if (n_frames == 0) return KOPEK_OK;
+    if (!d_frames || !d_out) return fail(KOPEK_ERR_INVALID, "NULL device pointer");
+    if (channels == 0) return fail(KOPEK_ERR_INVALID, "channels must be >= 1");
+    if ((uintptr_t)d_frames % 4 || (uintptr_t)d_out % 4) return fail(KOPEK_ERR_INVALID, "misaligned device pointer");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(KOPEK_ERR_CUDA, "cannot select device %d", device);
+    int sms = 0;
+    KOPEK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const unsigned grid = (unsigned)std::min<uint64_t>((n_frames + 255) / 256, (uint64_t)sms * 16);
+    f32_downmix_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(d_frames, n_frames, channels, d_out);
     KOPEK_CUDA(cudaGetLastError());
     return KOPEK_OK;
 }

@@ -89,6 +89,11 @@ def pcm16_scale_f32_device(d_pcm: int, n_values: int, factor: float, d_out: int,
     check(_lib.load().kopek_pcm16_scale_f32(d_pcm, n_values, factor, d_out, device, stream or None))
 
 
+def f32_downmix_device(d_frames: int, n_frames: int, channels: int, d_out: int, device: int = 0, stream: int = 0) -> None:
+    """kopek_f32_downmix: (f[0] + f[1]) / channels per interleaved frame (examples/pong/audio.rs:57-70)."""
+    check(_lib.load().kopek_f32_downmix(d_frames, n_frames, channels, d_out, device, stream or None))
+
+
 def detect_bpm_device(d_frames: int, n_frames: int, sample_rate: float = 44100.0, d_block_e: int = 0, d_avg_e: int = 0,
                       device: int = 0, stream: int = 0):
     """kopek_detect_bpm: kopek::decoder::detect_bpm (src/decoder.rs:39-71) on device-resident [n][2] i16 frames.

@@ -63,6 +63,7 @@ def lib() -> C.CDLL:
         L.oracle_max_threads.restype = i32
         L.oracle_pcm16_to_f32.argtypes = [vp, sz, sz, sz, f64, vp]
         L.oracle_pcm16_scale_f32.argtypes = [vp, sz, f32, vp]
+        L.oracle_f32_downmix.argtypes = [vp, sz, sz, vp]
         L.oracle_detect_bpm.restype = C.c_int64
         L.oracle_detect_bpm.argtypes = [vp, sz, f32, vp, vp, vp]
         _lib = L
@@ -214,6 +215,14 @@ def pcm16_scale_f32(pcm, factor: float = 0.00002) -> np.ndarray:
     pcm = np.ascontiguousarray(pcm, dtype=np.int16).reshape(-1)
     out = np.empty(pcm.size, dtype=np.float32)
     lib().oracle_pcm16_scale_f32(_p(pcm), pcm.size, factor, _p(out))
+    return out
+
+
+def f32_downmix(frames, channels: int) -> np.ndarray:
+    """examples/pong/audio.rs:57-70: (0.0 + f[0] + f[1]) / channels per interleaved frame."""
+    f = np.ascontiguousarray(frames, dtype=np.float32).reshape(-1, channels)
+    out = np.empty(f.shape[0], dtype=np.float32)
+    lib().oracle_f32_downmix(_p(f), f.shape[0], channels, _p(out))
     return out
 
 

@@ -403,6 +403,16 @@ ORACLE_API void oracle_pcm16_scale_f32(const int16_t *pcm, size_t n_values, floa
     for (size_t i = 0; i < n_values; ++i) out[i] = factor * (float)pcm[i];
 }
 
+/* the capture callback of examples/pong/audio.rs:57-70: for frame in data.chunks(channel_count) { average = 0.0; for
+ * sample in frame.iter().take(2) { average += sample; } average = average / frame.len() as f32; push(average) } */
+ORACLE_API void oracle_f32_downmix(const float *frames, size_t n_frames, size_t channels, float *out) {
+    for (size_t i = 0; i < n_frames; ++i) {
+        float average = 0.0f;
+        for (size_t c = 0; c < channels && c < 2; ++c) average += frames[i * channels + c];
+        out[i] = average / (float)channels;
+    }
+}
+
 /* detect_bpm, src/decoder.rs:39-71, statement by statement.
  *   f_frames = frames.map(|f| [f[0] as f32 / i16::MAX as f32, f[1] as f32 / i16::MAX as f32])     :41-44
  *   duration = (frames.len() as f32 / sample_rate) as usize                                        :46 (:35-37)

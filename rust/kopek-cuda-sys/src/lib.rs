@@ -87,6 +87,8 @@ extern "C" {
                               d_out: *mut f32, device: c_int, cuda_stream: *mut c_void) -> kopek_status;
     pub fn kopek_pcm16_scale_f32(d_pcm: *const i16, n_values: u64, factor: f32, d_out: *mut f32, device: c_int,
                                  cuda_stream: *mut c_void) -> kopek_status;
+    pub fn kopek_f32_downmix(d_frames: *const f32, n_frames: u64, channels: u32, d_out: *mut f32, device: c_int,
+                             cuda_stream: *mut c_void) -> kopek_status;
     pub fn kopek_detect_bpm(d_frames: *const i16, n_frames: u64, sample_rate: f32, bpm_out: *mut u32,
                             beats_out: *mut u32, d_block_e: *mut f32, d_avg_e: *mut f32, device: c_int,
                             cuda_stream: *mut c_void) -> kopek_status;

@@ -148,3 +148,25 @@ def test_pcm16_scale_f32_is_bit_exact(built_lib, oracle_mod):
     # the numpy statement of the same expression (f32 product) agrees with the oracle
     want = np.float32(0.00002) * allv.astype(np.float32)
     assert np.array_equal(oracle_mod.pcm16_scale_f32(allv, 0.00002).view(np.uint32), want.view(np.uint32))
+
+
+def test_f32_downmix_is_bit_exact(built_lib, oracle_mod):
+    """The pong capture callback (examples/pong/audio.rs:57-70): first two channels summed from 0.0, divided by the channel
+    count -- mono, stereo (aligned and not), four channels; signed zeros, infinities and NaN go the reference's way."""
+    import torch
+    from kopek_b200 import fft
+    rng = np.random.default_rng(4)
+    for channels, n, offset in ((2, 100_001, 0), (2, 5000, 1), (1, 4097, 0), (4, 3001, 0), (3, 7, 0)):
+        f = rng.standard_normal((n + offset, channels)).astype(np.float32)
+        f[offset:offset + 4, 0] = [-0.0, np.inf, np.nan, 1e-45]
+        f[offset:offset + 4, -1] = [-0.0, -np.inf, 1.0, -1e-45]
+        d = torch.from_numpy(f).cuda()
+        out = torch.full((n + 8,), 7.0, device="cuda")
+        fft.f32_downmix_device(d.data_ptr() + 4 * channels * offset, n, channels, out.data_ptr())
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        want = oracle_mod.f32_downmix(f[offset:], channels)
+        nan = np.isnan(want)
+        assert np.array_equal(np.isnan(got[:n]), nan)                        # NaN where the reference gives NaN (payloads differ by ISA)
+        assert np.array_equal(got[:n][~nan].view(np.uint32), want[~nan].view(np.uint32)), (channels, n, offset)
+        assert (got[n:] == 7.0).all()

@@ -248,3 +248,11 @@ def test_load_track_scaling(oracle_mod):
     got = oracle_mod.pcm16_scale_f32(allv, 0.00002)
     assert np.array_equal(got.view(np.uint32), (np.float32(0.00002) * allv.astype(np.float32)).view(np.uint32))
     assert got[32768] == 0.0 and got[-1] == np.float32(0.00002) * np.float32(32767)
+
+
+def test_capture_downmix(oracle_mod):
+    """examples/pong/audio.rs:57-70: the FIRST TWO channels are summed, the sum is divided by ALL channels."""
+    f = np.array([[1.0, 3.0, 100.0, 100.0], [-0.0, -0.0, 5.0, 5.0]], dtype=np.float32)
+    got = oracle_mod.f32_downmix(f, 4)
+    assert got[0] == 1.0 and got[1] == 0.0 and not np.signbit(got[1])       # 0.0 + -0.0 = +0.0
+    assert oracle_mod.f32_downmix(np.array([2.5, -1.5], dtype=np.float32), 1).tolist() == [2.5, -1.5]
