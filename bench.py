@@ -258,7 +258,7 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------- parity helpers ----
-def parity_against_oracle(got, samples, n, hop, window, output):
+def parity_against_oracle(got, samples, n, hop, window, output, full=False):
     """got: [frames, n/2+1] of the GPU path (|X|, |X|^2 or dB) for the frames of `samples`; compared in the linear
     domain with the f64 and the f32 instantiation of the restated recursion (north_star: 1e-5 * log2 N per bin relative
     to the frame's largest bin; peak bins equal, a near-tie closer than the tolerance is not a mismatch)."""
@@ -275,13 +275,15 @@ def parity_against_oracle(got, samples, n, hop, window, output):
     res = {"frames_checked": int(got.shape[0]), "tolerance": tol}
     ref64 = None
     for prec in (64, 32):
-        ref = np.abs(oracle.stft_complex(samples, n, hop, win, precision=prec, threads=oracle.max_threads()))
+        ref = np.abs(oracle.stft_complex(samples, n, hop, win, bins=n if full else None, precision=prec,
+                                         threads=oracle.max_threads()))
         den = ref.max(axis=1, keepdims=True)
         den[den == 0] = 1.0
         res[f"max_rel_err_vs_f{prec}_oracle"] = float((np.abs(got - ref) / den).max())
         if prec == 64:
             ref64 = ref
-    pg, pr = got.argmax(axis=1), ref64.argmax(axis=1)
+    half = n // 2 + 1                                         # peaks over bins 0..N/2 (the mirror repeats them)
+    pg, pr = got[:, :half].argmax(axis=1), ref64[:, :half].argmax(axis=1)
     bad = 0
     for f in np.nonzero(pg != pr)[0]:
         top = ref64[f, pr[f]]
@@ -405,14 +407,14 @@ def bench_config_cfg0(c):
 
 
 def bench_stft_config(c, name, n, hop, window, output, samples_dev, frames_expected, kernel, workload, check_frames,
-                      reps=20, copies=1):
+                      reps=20, copies=1, full=False):
     """Times one plan over device-resident samples (`copies` > 1 rotates through as many input/output buffer pairs so
     that a working set smaller than L2 is not re-read from it) and checks a slice against the oracle."""
     torch = c.torch
     from kopek_b200 import StftPlan
-    bins = n // 2 + 1
+    bins = n if full else n // 2 + 1
     stream = torch.cuda.current_stream().cuda_stream
-    with StftPlan(n, hop, window, output, device=c.local) as plan:
+    with StftPlan(n, hop, window, output, bins=1 if full else 0, device=c.local) as plan:
         ins = [samples_dev] + [samples_dev.clone() for _ in range(copies - 1)]
         outs = [torch.empty((frames_expected, bins), device=c.device, dtype=torch.float32) for _ in range(copies)]
 
@@ -437,7 +439,7 @@ def bench_stft_config(c, name, n, hop, window, output, samples_dev, frames_expec
             k = min(check_frames, frames_expected)
             ns = (k - 1) * hop + n
             res["parity"] = parity_against_oracle(outs[0][:k].cpu().numpy(), samples_dev[:ns].cpu().numpy(), n, hop,
-                                                  window, output)
+                                                  window, output, full=full)
         del ins, outs
     return res
 
@@ -650,6 +652,22 @@ def run_ours(args):
         r2["frac_per_gpu"] = r2["frac"]
         configs["cfg2"] = r2
         del noise
+        # the modes the reference's callers actually iterate (examples/graph/utils.rs:47-63 walks ALL N bins) and the
+        # unaligned case, on the headline frame size: every rank runs them on 2^19 frames, max over ranks reported
+        xm = synth(1 << 19, N_FFT, (1 << 24) + rank * (1 << 19), **m_kw)
+        configs["full_rows_1024"] = bench_stft_config(
+            c, "full_rows_1024", N_FFT, N_FFT, WINDOW_RECT, OUT_MAG, xm, 1 << 19,
+            "k1w_1024b_kernel<MAG,rect,FULL> (mirror stored beside the computed half)",
+            "FULL rows: 2^19 frames x 1024-pt rect |X|, all 1024 bins per row (what graph/pong iterate)", check_frames=128,
+            full=True)
+        hop_odd = N_FFT - 1
+        fr_odd = 1 + (xm.numel() - N_FFT) // hop_odd
+        configs["odd_hop_1024"] = bench_stft_config(
+            c, "odd_hop_1024", N_FFT, hop_odd, WINDOW_HANN, OUT_MAG, xm, fr_odd,
+            "k1w_1024b_kernel<MAG,WIN,VEC=false> (32-bit sample loads)",
+            f"odd hop: {fr_odd} frames x 1024-pt Hann |X|, hop 1023 (frames start at any 4-byte aligned sample)",
+            check_frames=128)
+        del xm
         # cfg3: one 2^24-point c2c f32 transform (four-step), rank 0's GPU; cuFFT on the same buffer beside it
         configs["cfg3"] = bench_cfg3(c) if rank == 0 else None
         barrier()
