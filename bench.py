@@ -760,6 +760,8 @@ def bench_cfg3(c):
     res["two_pass_ceiling_frac"] = 0.5
     res["l2"] = "input + workspace + output = 403 MB > 126 MB L2"
     res["cufft_note"] = "torch.fft.fft on the same complex64 buffer (cuFFT C2C f32): the library bar, never the product"
+    res["timing"] = ("20 eager back-to-back calls per size, CUDA events; the same calls replayed from a CUDA graph (no host "
+                     "work between launches) are in profiles/r2_k3_small_sizes.txt")
     # the oracle itself at a size it finishes in seconds: 2^16 points through the same four-step kernels
     n = 1 << 16
     rng = np.random.default_rng(7)

@@ -34,6 +34,17 @@
 
 namespace kopek {
 
+// Resident CTAs per SM asked of the compiler for the small tiles (N <= 1024: n <= 2^21).  There a pass is one or two
+// rounds of tiles (2^20: 512 pass-1 tiles on 444 slots, 256 pass-2 tiles on 148), and asking for four / two CTAs per SM
+// so that every tile finds a slot in the first round was measured (profiles/r2_k3_small_sizes.txt): 128 registers
+// instead of 143 / 188 cost 24-40 bytes of spills and the passes get SLOWER (2^20 in a CUDA graph 14.0 -> 14.9 us,
+// 2^19 9.4 -> 11.6 us) -- the tile's own latency chain, not the second round, is what a small transform waits for.
+#ifndef KOPEK_K3_MINB1
+#define KOPEK_K3_MINB1 2
+#endif
+#ifndef KOPEK_K3_MINB2
+#define KOPEK_K3_MINB2 1
+#endif
 template <int M> struct K3Cfg;
 template <> struct K3Cfg<256>  { static constexpr int R0 = 16, R1 = 16, R2 = 1; };
 template <> struct K3Cfg<512>  { static constexpr int R0 = 8,  R1 = 8,  R2 = 8; };
@@ -243,7 +254,7 @@ template <int KEEP> struct K3Out1 {
 // ---- pass 1: column tiles s (columns 2s, 2s+1), all n1.  Two-column tiles (N1 x 16 B = 64 KB at N1 = 4096)
 // let TWO CTAs share an SM, so one transforms while the other waits on shared memory or on its TMA traffic.
 template <int N1, int KEEP>
-__global__ void __launch_bounds__(N1 / 8, 2)
+__global__ void __launch_bounds__(N1 / 8, N1 <= 1024 ? KOPEK_K3_MINB1 : 2)
 k3_pass1(const __grid_constant__ CUtensorMap in_map, float2 *__restrict__ mid, K3Tables tb, int n_tiles) {
     extern __shared__ __align__(128) unsigned char k3_smem[];
     float2 *buf = reinterpret_cast<float2 *>(k3_smem);                 // N1 x 2 complex, dense
@@ -256,6 +267,12 @@ k3_pass1(const __grid_constant__ CUtensorMap in_map, float2 *__restrict__ mid, K
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    // pass 1 is itself launched with programmatic serialization: everything above (tables are never written by a
+    // kernel) may overlap the tail of whatever precedes it in the stream -- typically pass 2 of the previous transform;
+    // the input and the workspace are touched only from here on
+    pdl_wait_primary();
+    if (threadIdx.x == 0) {
         if ((int)blockIdx.x < n_tiles) {
             mbar_expect_tx(bar, N1 * 16);
             for (int r0 = 0; r0 < N1; r0 += 256) tma_load_2d(buf + r0 * 2, &in_map, 4 * blockIdx.x, r0, bar);
@@ -297,7 +314,7 @@ struct K3Out2 {
 
 // ---- pass 2: row tiles u (rows k1 = 4u..4u+3), all n2; block mid[u] is contiguous
 template <int N2>
-__global__ void __launch_bounds__(N2 / 4, 1)
+__global__ void __launch_bounds__(N2 / 4, N2 <= 1024 ? KOPEK_K3_MINB2 : 1)
 k3_pass2(const float2 *__restrict__ mid, float2 *__restrict__ outp, K3Tables tb, int n_tiles, int keep_from_tile) {
     extern __shared__ __align__(128) unsigned char k3_smem[];
     float2 *buf = reinterpret_cast<float2 *>(k3_smem);
@@ -328,6 +345,7 @@ k3_pass2(const float2 *__restrict__ mid, float2 *__restrict__ outp, K3Tables tb,
     uint32_t phase = 0;
     for (int v = blockIdx.x; v < n_tiles; v += gridDim.x) {
         const int u = n_tiles - 1 - v;
+        if (v + (int)gridDim.x >= n_tiles) pdl_launch_dependents();   // last tile: the next kernel may bring its prologue in
         mbar_wait(bar, phase);
         phase ^= 1;
         // the tile is in shared memory: a kept tile's lines are dead in L2 (one line per thread: N2 * 32 / 128 = N2 / 4)
@@ -386,6 +404,7 @@ k3_pass2_r64(const float2 *__restrict__ mid, float2 *__restrict__ outp, const fl
     uint32_t phase = 0;
     for (int tv = blockIdx.x; tv < n_tiles; tv += gridDim.x) {
         const int u = n_tiles - 1 - tv;
+        if (tv + (int)gridDim.x >= n_tiles) pdl_launch_dependents();  // last tile: the next kernel may bring its prologue in
         mbar_wait(bar, phase);
         phase ^= 1;
         if (u >= keep_from_tile) {                                    // the tile has landed: its 1024 lines are dead in L2
@@ -464,6 +483,9 @@ struct K3Plan {
     int n1 = 0, n2 = 0;
     float2 *tw1 = nullptr, *tw2 = nullptr, *hi = nullptr, *lo = nullptr;
     float2 *tw2r = nullptr;    // N2 = 4096: stage table of the two-stage radix-64 pass 2
+    // launch geometry, fixed when the plan is made (function attributes and occupancy are per device, like the plan):
+    // a call then costs one tensor-map encode, the workspace allocation and the two launches on the host
+    int sms = 0, grid1[3] = {0, 0, 0}, grid2 = 0;
 };
 // Tables only: one entry per (n, device), at most 9 lengths per device, kept for the life of the process, so a plan
 // handed out under the lock stays valid however many threads and streams call in.  The pass-1 -> pass-2 workspace
@@ -526,6 +548,8 @@ static void fill_twiddles(std::vector<float2> &v, uint64_t count, uint64_t step,
     }
 }
 
+static cudaError_t k3_prepare(K3Plan &p);
+
 static kopek_status k3_get_plan(uint64_t n, int device, K3Plan *out) {
     std::lock_guard<std::mutex> lk(g_k3_mu);
     for (const K3Plan &p : g_k3_plans)
@@ -559,6 +583,12 @@ static kopek_status k3_get_plan(uint64_t n, int device, K3Plan *out) {
         return fail(KOPEK_ERR_NOMEM, "four-step tables for n=%llu: %s", (unsigned long long)n,
                     cudaGetErrorString(cudaGetLastError()));
     }
+    cudaError_t pe = k3_prepare(p);
+    if (pe != cudaSuccess) {
+        cudaFree(p.tw1); cudaFree(p.tw2); cudaFree(p.hi); cudaFree(p.lo); cudaFree(p.tw2r);
+        cudaGetLastError();
+        return fail(KOPEK_ERR_CUDA, "four-step kernels for n=%llu: %s", (unsigned long long)n, cudaGetErrorString(pe));
+    }
     g_k3_plans.push_back(p);
     *out = p;
     return KOPEK_OK;
@@ -588,27 +618,68 @@ template <class K> static int k3_grid(K kern, int threads, int smem, int tiles, 
     long long g = (long long)nb * sms;
     return (int)(g < tiles ? g : tiles);
 }
-template <int N1, int KEEP> static cudaError_t launch_pass1k(int tiles, int sms, const CUtensorMap &a, float2 *mid,
-                                                             K3Tables tb, cudaStream_t st) {
+// prepare_*: opt the kernel into its shared-memory size on the current device and size the persistent grid (once per plan)
+template <int N1, int KEEP> static cudaError_t prepare_pass1k(int tiles, int sms, int *grid) {
     const int smem = N1 * 24 + 16;
     cudaError_t e = cudaFuncSetAttribute(k3_pass1<N1, KEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    k3_pass1<N1, KEEP><<<k3_grid(k3_pass1<N1, KEEP>, N1 / 8, smem, tiles, sms), N1 / 8, smem, st>>>(a, mid, tb, tiles);
-    return cudaGetLastError();
+    if (e == cudaSuccess) *grid = k3_grid(k3_pass1<N1, KEEP>, N1 / 8, smem, tiles, sms);
+    return e;
 }
-template <int N1> static cudaError_t launch_pass1(int tiles, int sms, const CUtensorMap &a, float2 *mid, K3Tables tb,
-                                                  int keep, cudaStream_t st) {
-    if (keep == 2) return launch_pass1k<N1, 2>(tiles, sms, a, mid, tb, st);
-    if (keep == 1) return launch_pass1k<N1, 1>(tiles, sms, a, mid, tb, st);
-    return launch_pass1k<N1, 0>(tiles, sms, a, mid, tb, st);
+template <int N1> static cudaError_t prepare_pass1(int tiles, int sms, int (&grid)[3]) {
+    cudaError_t e = prepare_pass1k<N1, 0>(tiles, sms, &grid[0]);
+    if (e == cudaSuccess) e = prepare_pass1k<N1, 1>(tiles, sms, &grid[1]);
+    if (e == cudaSuccess) e = prepare_pass1k<N1, 2>(tiles, sms, &grid[2]);
+    return e;
 }
-template <int N2> static cudaError_t launch_pass2(int tiles, int sms, const float2 *mid, float2 *o, K3Tables tb,
-                                                  int keep_from_tile, cudaStream_t st) {
+template <int N2> static cudaError_t prepare_pass2(int tiles, int sms, int *grid) {
     const int smem = N2 * 40 + 16;
     cudaError_t e = cudaFuncSetAttribute(k3_pass2<N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) *grid = k3_grid(k3_pass2<N2>, N2 / 4, smem, tiles, sms);
+    return e;
+}
+static const bool k3_chain = !(getenv("KOPEK_K3_CHAIN") && atoi(getenv("KOPEK_K3_CHAIN")) == 0);   // tuning switch
+static const bool k3_use_r64 = !(getenv("KOPEK_K3_R64") && atoi(getenv("KOPEK_K3_R64")) == 0);   // tuning switch
+static cudaError_t k3_prepare(K3Plan &p) {
+    cudaError_t e = cudaDeviceGetAttribute(&p.sms, cudaDevAttrMultiProcessorCount, p.device);
     if (e != cudaSuccess) return e;
-    return launch_pdl(k3_pass2<N2>, k3_grid(k3_pass2<N2>, N2 / 4, smem, tiles, sms), N2 / 4, (size_t)smem, st, mid, o, tb, tiles,
-                      keep_from_tile);
+    const int t1 = p.n2 / 2, t2 = p.n1 / 4;
+    switch (p.n1) {
+        case 256: e = prepare_pass1<256>(t1, p.sms, p.grid1); break;
+        case 512: e = prepare_pass1<512>(t1, p.sms, p.grid1); break;
+        case 1024: e = prepare_pass1<1024>(t1, p.sms, p.grid1); break;
+        case 2048: e = prepare_pass1<2048>(t1, p.sms, p.grid1); break;
+        default: e = prepare_pass1<4096>(t1, p.sms, p.grid1); break;
+    }
+    if (e != cudaSuccess) return e;
+    switch (p.n2) {
+        case 256: return prepare_pass2<256>(t2, p.sms, &p.grid2);
+        case 512: return prepare_pass2<512>(t2, p.sms, &p.grid2);
+        case 1024: return prepare_pass2<1024>(t2, p.sms, &p.grid2);
+        case 2048: return prepare_pass2<2048>(t2, p.sms, &p.grid2);
+        default:
+            if (k3_use_r64) {
+                p.grid2 = t2 < p.sms ? t2 : p.sms;
+                return cudaFuncSetAttribute(k3_pass2_r64, cudaFuncAttributeMaxDynamicSharedMemorySize, K3R_SMEM);
+            }
+            return prepare_pass2<4096>(t2, p.sms, &p.grid2);
+    }
+}
+
+template <int N1, int KEEP> static cudaError_t launch_pass1k(const K3Plan &p, const CUtensorMap &a, float2 *mid, K3Tables tb,
+                                                             cudaStream_t st) {
+    if (k3_chain) return launch_pdl(k3_pass1<N1, KEEP>, p.grid1[KEEP], N1 / 8, (size_t)(N1 * 24 + 16), st, a, mid, tb, p.n2 / 2);
+    k3_pass1<N1, KEEP><<<p.grid1[KEEP], N1 / 8, N1 * 24 + 16, st>>>(a, mid, tb, p.n2 / 2);
+    return cudaGetLastError();
+}
+template <int N1> static cudaError_t launch_pass1(const K3Plan &p, const CUtensorMap &a, float2 *mid, K3Tables tb, int keep,
+                                                  cudaStream_t st) {
+    if (keep == 2) return launch_pass1k<N1, 2>(p, a, mid, tb, st);
+    if (keep == 1) return launch_pass1k<N1, 1>(p, a, mid, tb, st);
+    return launch_pass1k<N1, 0>(p, a, mid, tb, st);
+}
+template <int N2> static cudaError_t launch_pass2(const K3Plan &p, const float2 *mid, float2 *o, K3Tables tb,
+                                                  int keep_from_tile, cudaStream_t st) {
+    return launch_pdl(k3_pass2<N2>, p.grid2, N2 / 4, (size_t)(N2 * 40 + 16), st, mid, o, tb, p.n1 / 4, keep_from_tile);
 }
 
 }  // namespace kopek
@@ -637,8 +708,6 @@ extern "C" kopek_status kopek_fft_large_c2c_f32(const float *d_in, float *d_out,
         return fail(KOPEK_ERR_CUDA, "cuTensorMapEncodeTiled failed (driver entry point missing or bad geometry)");
     K3Tables tb{p.tw1, p.tw2, p.hi, p.lo};
     cudaStream_t stream = (cudaStream_t)cuda_stream;
-    int sms = 0;
-    KOPEK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     // workspace between the passes: this call's own, ordered on the caller's stream (allocation, both passes, release)
     cudaMemPool_t pool = nullptr;
     if ((st = k3_workspace_pool(device, &pool)) != KOPEK_OK) return st;
@@ -662,32 +731,26 @@ extern "C" kopek_status kopek_fft_large_c2c_f32(const float *d_in, float *d_out,
     const int keep_from = (keep == 2 ? 0 : keep == 1 ? tiles2 / 2 : tiles2 + 1) * 4;     // in rows; the launches take tiles
     e = cudaErrorInvalidValue;
     switch (p.n1) {
-        case 256: e = launch_pass1<256>(p.n2 / 2, sms, in_map, mid, tb, keep, stream); break;
-        case 512: e = launch_pass1<512>(p.n2 / 2, sms, in_map, mid, tb, keep, stream); break;
-        case 1024: e = launch_pass1<1024>(p.n2 / 2, sms, in_map, mid, tb, keep, stream); break;
-        case 2048: e = launch_pass1<2048>(p.n2 / 2, sms, in_map, mid, tb, keep, stream); break;
-        case 4096: e = launch_pass1<4096>(p.n2 / 2, sms, in_map, mid, tb, keep, stream); break;
+        case 256: e = launch_pass1<256>(p, in_map, mid, tb, keep, stream); break;
+        case 512: e = launch_pass1<512>(p, in_map, mid, tb, keep, stream); break;
+        case 1024: e = launch_pass1<1024>(p, in_map, mid, tb, keep, stream); break;
+        case 2048: e = launch_pass1<2048>(p, in_map, mid, tb, keep, stream); break;
+        case 4096: e = launch_pass1<4096>(p, in_map, mid, tb, keep, stream); break;
     }
     if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "four-step pass 1 (N1=%d): %s", p.n1, cudaGetErrorString(e));
+    float2 *o = reinterpret_cast<float2 *>(d_out);
     switch (p.n2) {
-        case 256: e = launch_pass2<256>(p.n1 / 4, sms, mid, reinterpret_cast<float2 *>(d_out), tb, keep_from / 4, stream); break;
-        case 512: e = launch_pass2<512>(p.n1 / 4, sms, mid, reinterpret_cast<float2 *>(d_out), tb, keep_from / 4, stream); break;
-        case 1024: e = launch_pass2<1024>(p.n1 / 4, sms, mid, reinterpret_cast<float2 *>(d_out), tb, keep_from / 4, stream); break;
-        case 2048: e = launch_pass2<2048>(p.n1 / 4, sms, mid, reinterpret_cast<float2 *>(d_out), tb, keep_from / 4, stream); break;
-        case 4096: {
-            static const bool r64 = !(getenv("KOPEK_K3_R64") && atoi(getenv("KOPEK_K3_R64")) == 0);   // tuning switch
-            if (r64) {
-                const int tiles = p.n1 / 4;
-                e = cudaFuncSetAttribute(k3_pass2_r64, cudaFuncAttributeMaxDynamicSharedMemorySize, K3R_SMEM);
-                if (e == cudaSuccess) {
-                    e = launch_pdl(k3_pass2_r64, tiles < sms ? tiles : sms, 256, (size_t)K3R_SMEM, stream, (const float2 *)mid,
-                                   reinterpret_cast<float2 *>(d_out), (const float2 *)p.tw2r, tiles, keep_from / 4);
-                }
-            } else {
-                e = launch_pass2<4096>(p.n1 / 4, sms, mid, reinterpret_cast<float2 *>(d_out), tb, keep_from / 4, stream);
-            }
+        case 256: e = launch_pass2<256>(p, mid, o, tb, keep_from / 4, stream); break;
+        case 512: e = launch_pass2<512>(p, mid, o, tb, keep_from / 4, stream); break;
+        case 1024: e = launch_pass2<1024>(p, mid, o, tb, keep_from / 4, stream); break;
+        case 2048: e = launch_pass2<2048>(p, mid, o, tb, keep_from / 4, stream); break;
+        case 4096:
+            if (k3_use_r64)
+                e = launch_pdl(k3_pass2_r64, p.grid2, 256, (size_t)K3R_SMEM, stream, (const float2 *)mid, o,
+                               (const float2 *)p.tw2r, p.n1 / 4, keep_from / 4);
+            else
+                e = launch_pass2<4096>(p, mid, o, tb, keep_from / 4, stream);
             break;
-        }
         default: e = cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "four-step pass 2 (N2=%d): %s", p.n2, cudaGetErrorString(e));

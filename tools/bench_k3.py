@@ -29,6 +29,30 @@ def timed(fn, iters=20, warm=3):
     return e0.elapsed_time(e1) / iters
 
 
+def graph_timed(fn, calls=20, reps=5):
+    """The same calls captured ONCE into a CUDA graph and replayed: device time per call with no host work between
+    launches (the eager figure includes whatever the host needs per call when that exceeds the kernels' time)."""
+    try:
+        side = torch.cuda.Stream()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(calls):
+                fn(torch.cuda.current_stream().cuda_stream)
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (reps * calls)
+    except Exception as ex:                                   # capture not possible: say so, keep the eager figures
+        torch.cuda.synchronize()
+        print(f"   (graph capture failed: {type(ex).__name__}: {str(ex)[:120]})")
+        return float("nan")
+
+
 print(f"KOPEK_K3_KEEP_MB={os.environ.get('KOPEK_K3_KEEP_MB', '(default)')} lib={os.environ.get('KOPEK_TUNE_TAG', 'production')}")
 for lg in sizes:
     n = 1 << lg
@@ -40,5 +64,7 @@ for lg in sizes:
     want = torch.fft.fft(a.to(torch.complex128))
     err = ((b.to(torch.complex128) - want).abs().max() / want.abs().max()).item()
     gbs = 2 * n * 8 / ms / 1e6
+    g_ms = graph_timed(lambda s_: fft.fft_large_device(a.data_ptr(), b.data_ptr(), n, 0, s_))
+    g_lib = graph_timed(lambda s_: torch.fft.fft(a))
     print(f"2^{lg}: {ms:.4f} ms  {gbs:7.1f} GB/s algorithmic {100 * gbs / PEAK:5.1f}%   cuFFT {lib:.4f} ms ({lib / ms:.2f}x)   "
-          f"max rel err vs f64 {err:.2e}", flush=True)
+          f"max rel err vs f64 {err:.2e}   | in a CUDA graph: {g_ms:.4f} ms, cuFFT {g_lib:.4f} ms ({g_lib / g_ms:.2f}x)", flush=True)
