@@ -120,6 +120,15 @@ static kopek_status close_enqueue(kopek_mgpu *c) {
     return KOPEK_OK;
 }
 
+// An entry point failed after open_window: the devices that did get work keep running, so the end events are still
+// recorded (best effort) -- a later kopek_mgpu_sync then drains the streams and finds both events of every device --
+// and the first error is what the caller sees.
+static kopek_status fail_in_window(kopek_mgpu *c, kopek_status st) {
+    const std::string msg(kopek_last_error());
+    close_enqueue(c);
+    return fail(st, "%s", msg.c_str());
+}
+
 static void mgpu_free(kopek_mgpu *c) {
     NcclApi &nc = nccl_api();
     for (MgpuDev &d : c->devs) {
@@ -257,7 +266,7 @@ kopek_status kopek_mgpu_exec(kopek_mgpu *ctx, const float *const *d_samples, con
         uint64_t nf = 0;
         st = kopek_stft_exec(d.plan, d_samples[r], n_samples[r], d_out[r], &nf, d.stream);
         if (n_frames_out) n_frames_out[r] = nf;
-        if (st != KOPEK_OK) return st;
+        if (st != KOPEK_OK) return fail_in_window(ctx, st);
     }
     return close_enqueue(ctx);
 }
@@ -279,7 +288,7 @@ kopek_status kopek_mgpu_exec_gathered(kopek_mgpu *ctx, const float *const *d_sam
         const bool bulk = d.plan_bulk && (uintptr_t)dst % 16 == 0;
         uint64_t nf = 0;
         st = kopek_stft_exec(bulk ? d.plan_bulk : d.plan, d_samples[r], n_samples[r], dst, &nf, d.stream);
-        if (st != KOPEK_OK) return st;
+        if (st != KOPEK_OK) return fail_in_window(ctx, st);
         row += nf;
     }
     if (n_frames_total) *n_frames_total = row;
@@ -301,7 +310,9 @@ kopek_status kopek_mgpu_gather(kopek_mgpu *ctx, void *const *d_out, const uint64
     MgpuDev &root = ctx->devs[0];
     if (n_frames[0] && d_out[0] != d_dst) {
         DeviceGuard g(root.device);
-        KOPEK_CUDA(cudaMemcpyAsync(d_dst, d_out[0], off[1], cudaMemcpyDeviceToDevice, root.stream));
+        cudaError_t e = cudaMemcpyAsync(d_dst, d_out[0], off[1], cudaMemcpyDeviceToDevice, root.stream);
+        if (e != cudaSuccess)
+            return fail_in_window(ctx, fail(KOPEK_ERR_CUDA, "gather: device %d's own rows: %s", root.device, cudaGetErrorString(e)));
     }
     if (mode == KOPEK_GATHER_COPY) {
         // pushed by the source device's stream: ordered after that device's transform, all links busy at once
@@ -309,8 +320,11 @@ kopek_status kopek_mgpu_gather(kopek_mgpu *ctx, void *const *d_out, const uint64
             if (!n_frames[r]) continue;
             MgpuDev &d = ctx->devs[r];
             DeviceGuard g(d.device);
-            KOPEK_CUDA(cudaMemcpyPeerAsync(static_cast<char *>(d_dst) + off[r], root.device, d_out[r], d.device,
-                                           off[r + 1] - off[r], d.stream));
+            cudaError_t e = cudaMemcpyPeerAsync(static_cast<char *>(d_dst) + off[r], root.device, d_out[r], d.device,
+                                                off[r + 1] - off[r], d.stream);
+            if (e != cudaSuccess)
+                return fail_in_window(ctx, fail(KOPEK_ERR_CUDA, "gather: peer copy %d -> %d: %s", d.device, root.device,
+                                                cudaGetErrorString(e)));
         }
     } else if (R > 1) {
         NcclApi &nc = nccl_api();
@@ -322,7 +336,8 @@ kopek_status kopek_mgpu_gather(kopek_mgpu *ctx, void *const *d_out, const uint64
             if (rc == 0) rc = nc.recv(static_cast<char *>(d_dst) + off[r], bytes, 1, (int)r, root.nccl, root.stream);
         }
         const int rc2 = nc.group_end();
-        if (rc != 0 || rc2 != 0) return fail(KOPEK_ERR_CUDA, "NCCL gather: %s", nc.errstr(rc ? rc : rc2));
+        if (rc != 0 || rc2 != 0)
+            return fail_in_window(ctx, fail(KOPEK_ERR_CUDA, "NCCL gather: %s", nc.errstr(rc ? rc : rc2)));
     }
     return close_enqueue(ctx);
 }
@@ -337,8 +352,9 @@ kopek_status kopek_mgpu_sync(kopek_mgpu *ctx, float *elapsed_ms_max) {
         KOPEK_CUDA(cudaStreamSynchronize(d.stream));
         if (ctx->window_open) {
             float ms = 0.0f;
-            KOPEK_CUDA(cudaEventElapsedTime(&ms, d.ev_begin, d.ev_end));
-            worst = std::max(worst, ms);
+            // after a failed entry point an end event may be missing: no time for that device, not an error of sync
+            if (cudaEventElapsedTime(&ms, d.ev_begin, d.ev_end) == cudaSuccess) worst = std::max(worst, ms);
+            else cudaGetLastError();
         }
     }
     ctx->window_open = false;

@@ -121,6 +121,32 @@ def test_mgpu_argument_errors(built_lib):
     assert lib.kopek_mgpu_destroy(None) == _lib.OK
 
 
+def test_failed_exec_leaves_the_context_usable(built_lib):
+    """An entry point that fails after the timing window was opened (here: a NULL shard pointer) must leave the
+    context in a state kopek_mgpu_sync accepts, and the next valid call must give the usual result."""
+    import torch
+
+    from kopek_b200 import StftPlan, _lib, signals
+    from kopek_b200.sharded import MultiGpuStft
+    devs = _devices(torch)
+    n, hop = 1024, 512
+    x = signals.white_noise(200_000, seed=11)
+    with StftPlan(n, hop, 1, 1, device=0) as plan:
+        ref = plan.exec_host(x)
+    with MultiGpuStft(devs, n, hop, 1, 1) as m:
+        lib = _lib.load()
+        R = len(devs)
+        ins = (C.c_void_p * R)(*([None] * R))                      # NULL sample pointers with a non-zero count
+        cnt = (C.c_uint64 * R)(*([4096] * R))
+        outs = (C.c_void_p * R)(*([None] * R))
+        assert lib.kopek_mgpu_exec(m._h, ins, cnt, outs, None) == _lib.ERR_INVALID
+        ms = C.c_float(-1.0)
+        assert lib.kopek_mgpu_sync(m._h, C.byref(ms)) == _lib.OK    # drains, reports, resets the window
+        got = m.exec_host(x)
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+        assert lib.kopek_mgpu_sync(m._h, C.byref(ms)) == _lib.OK
+
+
 def test_custom_window_on_every_device(built_lib):
     """kopek_mgpu_set_custom_window uploads the coefficients to every device's plan."""
     import torch
