@@ -112,3 +112,49 @@ def test_exec_host_chunks_are_sized_by_the_busier_direction(built_lib):
         # every 1024th frame is a frame of the coarse plan (another kernel: same values to rounding)
         assert got.shape[0] == 20001 and ref.shape[0] == 20
         assert np.abs(got[::1024][:20] - ref).max() <= 1e-5 * 12 * ref.max()
+
+
+@pytest.mark.parametrize("n,hop,output", [(1024, 1024, 1), (4096, 4096, 1), (256, 256, 0)])
+def test_sample_and_byte_offsets_beyond_32_bits(built_lib, n, hop, output):
+    """Maximum sizes: one call over MORE than 2^32 samples (17 GB of f32) whose output crosses 2^32 bytes (and, for the
+    complex rows, 2^32 elements too).  The signal is zero except for a handful of frames around the 2^32-sample and
+    2^32-byte marks and at the very end; those rows must equal the rows of the same frames transformed on their
+    own, every row between them must be exactly zero, and nothing may land outside the output."""
+    import torch
+
+    from kopek_b200 import StftPlan, signals
+    free, _ = torch.cuda.mem_get_info()
+    frames = (1 << 32) // hop + 37
+    ns = (frames - 1) * hop + n
+    with StftPlan(n, hop, 1, output, device=0) as plan:
+        row = plan.pitch * (2 if output == 0 else 1)                  # f32 values per row
+        need = ns * 4 + frames * row * 4 + (2 << 30)
+        if free < need:
+            pytest.skip(f"needs {need >> 30} GiB of device memory")
+        x = torch.zeros(ns, device="cuda", dtype=torch.float32)
+        # frames of interest: around sample 2^32, around output byte 2^32, and the last ones
+        f_byte = (1 << 32) // (row * 4)
+        marks = sorted({0, 1, f_byte - 1, f_byte, f_byte + 1, (1 << 32) // hop - 1, (1 << 32) // hop, frames - 2, frames - 1})
+        tone = torch.from_numpy(signals.sine_frames(len(marks), n)).cuda().view(len(marks), n)
+        for i, f in enumerate(marks):
+            x[f * hop:f * hop + n] = tone[i]
+        out = torch.full((frames * row + 2 * GUARD,), SENT, device="cuda", dtype=torch.float32)
+        got = plan.exec_ptr(x.data_ptr(), ns, out[GUARD:].data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert got == frames
+        small = torch.empty((len(marks), row), device="cuda", dtype=torch.float32)
+        plan.exec_ptr(tone.data_ptr(), tone.numel(), small.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        used = plan.bins * (2 if output == 0 else 1)
+    body = out[GUARD:GUARD + frames * row].view(frames, row)
+    assert torch.equal(out[:GUARD], torch.full_like(out[:GUARD], SENT))
+    assert torch.equal(out[GUARD + frames * row:], torch.full_like(out[:GUARD], SENT))
+    for i, f in enumerate(marks):
+        assert torch.equal(body[f, :used].view(torch.int32), small[i, :used].view(torch.int32)), f"frame {f}"
+    # everything else is the transform of silence: exactly zero (checked in slabs to bound the temporaries)
+    keep = torch.ones(frames, dtype=torch.bool, device="cuda")
+    keep[torch.tensor(marks, device="cuda")] = False
+    step = 1 << 18
+    for f0 in range(0, frames, step):
+        blk = body[f0:f0 + step, :used]
+        assert not bool((blk[keep[f0:f0 + step]] != 0).any()), f"non-zero row in frames {f0}.."
