@@ -22,4 +22,4 @@ for blk in blocks[1:]:
     loop = [t for a, t in ins if best[1] <= a <= best[2]]
     c = collections.Counter(re.sub(r"^@!?U?P\d+\s+", "", t).split()[0].split(".")[0] for t in loop)
     regs = re.search(r"REG:(\d+)", subprocess.run(["cuobjdump", "-res-usage", lib], capture_output=True, text=True).stdout.split(name)[1]) if False else None
-    print(f"{name}\n  total {len(ins)}  loop {len(loop)}  " + " ".join(f"{k}:{v}" for k, v in c.most_common(14)))
+    print(f"{name}\n  total {len(ins)}  loop {len(loop)}  " + " ".join(f"{k}:{v}" for k, v in c.most_common(40)))
