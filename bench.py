@@ -328,6 +328,29 @@ def time_launches(torch, fn, reps, warm=3):
     return e0.elapsed_time(e1) / reps
 
 
+def time_graph_replays(torch, fn, calls=20, reps=5):
+    """`fn(stream)` captured `calls` times into ONE CUDA graph and replayed `reps` times: device time per call with no
+    host work between the launches.  None when the capture is not possible (never fatal to the bench line)."""
+    try:
+        side = torch.cuda.Stream()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+            for _ in range(calls):
+                fn(torch.cuda.current_stream().cuda_stream)
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (reps * calls)
+    except Exception:
+        torch.cuda.synchronize()
+        return None
+
+
 def max_over_ranks(c, value: float) -> float:
     if c.world == 1:
         return value
@@ -748,10 +771,15 @@ def bench_cfg3(c):
         o = torch.empty_like(a)
         ms = time_launches(torch, lambda i: fft.fft_large_device(a.data_ptr(), o.data_ptr(), n, c.local, stream), 20)
         lib_ms = time_launches(torch, lambda i: torch.fft.fft(a), 20)
+        g_ms = g_lib = None
+        if c.world == 1:            # (a capture beside live NCCL communicators is not worth the risk to the line)
+            g_ms = time_graph_replays(torch, lambda st: fft.fft_large_device(a.data_ptr(), o.data_ptr(), n, c.local, st))
+            g_lib = time_graph_replays(torch, lambda st: torch.fft.fft(a))
         want = torch.fft.fft(a.to(torch.complex128))
         err = float(((o.to(torch.complex128) - want).abs().max() / want.abs().max()).item())
         sizes[f"2^{lg}"] = {"ms": ms, "cufft_c2c_f32_ms": lib_ms, "speed_vs_cufft": lib_ms / ms,
                             "max_rel_err_vs_f64_library": err,
+                            "graph_replay_ms": g_ms, "cufft_graph_replay_ms": g_lib,
                             "achieved_gbs": 2 * n * 8 / (ms * 1e-3) / 1e9, "frac": 2 * n * 8 / (ms * 1e-3) / 1e9 / c.peak}
         del a, o, want
     res["sizes"] = sizes
@@ -760,8 +788,8 @@ def bench_cfg3(c):
     res["two_pass_ceiling_frac"] = 0.5
     res["l2"] = "input + workspace + output = 403 MB > 126 MB L2"
     res["cufft_note"] = "torch.fft.fft on the same complex64 buffer (cuFFT C2C f32): the library bar, never the product"
-    res["timing"] = ("20 eager back-to-back calls per size, CUDA events; the same calls replayed from a CUDA graph (no host "
-                     "work between launches) are in profiles/r2_k3_small_sizes.txt")
+    res["timing"] = ("ms / cufft_c2c_f32_ms: 20 eager back-to-back calls per size, CUDA events; graph_replay_ms: the same "
+                     "calls captured into one CUDA graph and replayed (no host work between launches; N = 1 only)")
     # the oracle itself at a size it finishes in seconds: 2^16 points through the same four-step kernels
     n = 1 << 16
     rng = np.random.default_rng(7)
