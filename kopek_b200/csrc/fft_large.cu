@@ -75,6 +75,22 @@ __device__ __forceinline__ void k3_stage(float2 *buf, const float2 *tw, int tid,
                                          const OUT &out = OUT()) {
     constexpr int NB = 16 / RAD;
     float2 d[16];
+    // The four table lookups of the inter-step twiddle do not depend on the tile.  For M < 4096 they are issued before
+    // the shared-memory reads, so that their L2 latency (the tables do not fit the L1 the tile buffers leave) hides
+    // behind the butterflies -- which also frees the compiler from the spills it had at 128 registers (M = 2048: STACK
+    // 40 -> 0; 2^22 41.4 -> 40.5 us, 2^23 79.9 -> 77.8 us).  At M = 4096 (64 registers) the four extra live values
+    // cost more than the latency they hide (2^24 124.3 -> 126.5 us in a graph): looked up late there.
+    constexpr bool XTW_EARLY = XTW && M < 4096;
+    float2 x_b0[NB], x_st[NB];
+    if constexpr (XTW_EARLY) {
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const int j = tid + T * i, kk = j & (NS - 1), base = (j - kk) * RAD + kk;
+            const uint32_t m0 = n2 * (uint32_t)base, ms = n2 * (uint32_t)NS;
+            x_b0[i] = cmul(__ldg(tw_hi + (m0 >> 12)), __ldg(tw_lo + (m0 & 4095u)));
+            x_st[i] = cmul(__ldg(tw_hi + (ms >> 12)), __ldg(tw_lo + (ms & 4095u)));
+        }
+    }
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
         int j = tid + T * i;
@@ -105,9 +121,14 @@ __device__ __forceinline__ void k3_stage(float2 *buf, const float2 *tw, int tid,
         if constexpr (XTW) {
             // outputs q = base + k NS: W_n^{n2 q} = W_n^{n2 base} (W_n^{n2 NS})^k -- two table lookups per
             // butterfly, the powers by squaring/multiplying (depth <= 4, error ~4 ulp)
-            const uint32_t m0 = n2 * (uint32_t)base, ms = n2 * (uint32_t)NS;
-            const float2 b0 = cmul(__ldg(tw_hi + (m0 >> 12)), __ldg(tw_lo + (m0 & 4095u)));
-            const float2 st = cmul(__ldg(tw_hi + (ms >> 12)), __ldg(tw_lo + (ms & 4095u)));
+            float2 b0, st;
+            if constexpr (XTW_EARLY) {
+                b0 = x_b0[i], st = x_st[i];
+            } else {
+                const uint32_t m0 = n2 * (uint32_t)base, ms = n2 * (uint32_t)NS;
+                b0 = cmul(__ldg(tw_hi + (m0 >> 12)), __ldg(tw_lo + (m0 & 4095u)));
+                st = cmul(__ldg(tw_hi + (ms >> 12)), __ldg(tw_lo + (ms & 4095u)));
+            }
             float2 pw[RAD];
             pw[0] = make_float2(1.0f, 0.0f);
             pw[1] = st;
