@@ -276,7 +276,8 @@ template <int KEEP> struct K3Out1 {
 // let TWO CTAs share an SM, so one transforms while the other waits on shared memory or on its TMA traffic.
 template <int N1, int KEEP>
 __global__ void __launch_bounds__(N1 / 8, N1 <= 1024 ? KOPEK_K3_MINB1 : 2)
-k3_pass1(const __grid_constant__ CUtensorMap in_map, float2 *__restrict__ mid, K3Tables tb, int n_tiles) {
+k3_pass1(const __grid_constant__ CUtensorMap in_map, float2 *__restrict__ mid, K3Tables tb, int n_tiles,
+         const float2 *__restrict__ in) {
     extern __shared__ __align__(128) unsigned char k3_smem[];
     float2 *buf = reinterpret_cast<float2 *>(k3_smem);                 // N1 x 2 complex, dense
     float2 *s_tw = reinterpret_cast<float2 *>(k3_smem + (size_t)N1 * 16);   // stage twiddles, N1 entries
@@ -306,6 +307,15 @@ k3_pass1(const __grid_constant__ CUtensorMap in_map, float2 *__restrict__ mid, K
         mbar_wait(bar, phase);
         phase ^= 1;
         const int nxt = s + gridDim.x;
+        // The next tile's TMA load can only be issued when this tile's last stage has read the buffer, and a quarter of
+        // the pass is spent waiting for it (ncu source view: the mbarrier wait).  With `in` set its DRAM latency is paid
+        // now instead: the eight tiles that share the 128-byte lines of a row are in flight on eight CTAs at the same
+        // time, so each of them asks L2 for the lines of one row in eight (one line per thread).  The host enables
+        // it where it was measured to pay (profiles/r2_k3_small_sizes.txt): 2^23, -6 %; at 2^24 the prefetched
+        // lines compete with the part of `mid` that is kept in L2, at <= 2^22 the benchmark's input is L2-resident.
+        if (in != nullptr && nxt < n_tiles)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(in + ((size_t)((nxt & 7) + 8 * (int)threadIdx.x) * (2 * (size_t)n_tiles) +
+                                                               (size_t)(nxt >> 3) * 16)));
         K3Out1<KEEP> out{mid + (size_t)s * 8 + c, (size_t)n_tiles * 8, bar, &in_map, buf, nxt < n_tiles ? nxt : -1, N1,
                          pol_keep, pol_stream};
         // sub-transform + inter-step twiddle W_n^{n2 k1}, n2 = 2s + c (applied in registers before the stores)
@@ -687,16 +697,17 @@ static cudaError_t k3_prepare(K3Plan &p) {
 }
 
 template <int N1, int KEEP> static cudaError_t launch_pass1k(const K3Plan &p, const CUtensorMap &a, float2 *mid, K3Tables tb,
-                                                             cudaStream_t st) {
-    if (k3_chain) return launch_pdl(k3_pass1<N1, KEEP>, p.grid1[KEEP], N1 / 8, (size_t)(N1 * 24 + 16), st, a, mid, tb, p.n2 / 2);
-    k3_pass1<N1, KEEP><<<p.grid1[KEEP], N1 / 8, N1 * 24 + 16, st>>>(a, mid, tb, p.n2 / 2);
+                                                             cudaStream_t st, const float2 *in) {
+    if (k3_chain)
+        return launch_pdl(k3_pass1<N1, KEEP>, p.grid1[KEEP], N1 / 8, (size_t)(N1 * 24 + 16), st, a, mid, tb, p.n2 / 2, in);
+    k3_pass1<N1, KEEP><<<p.grid1[KEEP], N1 / 8, N1 * 24 + 16, st>>>(a, mid, tb, p.n2 / 2, in);
     return cudaGetLastError();
 }
 template <int N1> static cudaError_t launch_pass1(const K3Plan &p, const CUtensorMap &a, float2 *mid, K3Tables tb, int keep,
-                                                  cudaStream_t st) {
-    if (keep == 2) return launch_pass1k<N1, 2>(p, a, mid, tb, st);
-    if (keep == 1) return launch_pass1k<N1, 1>(p, a, mid, tb, st);
-    return launch_pass1k<N1, 0>(p, a, mid, tb, st);
+                                                  cudaStream_t st, const float2 *in) {
+    if (keep == 2) return launch_pass1k<N1, 2>(p, a, mid, tb, st, in);
+    if (keep == 1) return launch_pass1k<N1, 1>(p, a, mid, tb, st, in);
+    return launch_pass1k<N1, 0>(p, a, mid, tb, st, in);
 }
 template <int N2> static cudaError_t launch_pass2(const K3Plan &p, const float2 *mid, float2 *o, K3Tables tb,
                                                   int keep_from_tile, cudaStream_t st) {
@@ -750,13 +761,17 @@ extern "C" kopek_status kopek_fft_large_c2c_f32(const float *d_in, float *d_out,
     const int keep = keep_mb <= 0 ? 0 : n * sizeof(float2) <= ((uint64_t)keep_mb << 20) ? 2 : 1;
     const int tiles2 = p.n1 / 4;
     const int keep_from = (keep == 2 ? 0 : keep == 1 ? tiles2 / 2 : tiles2 + 1) * 4;     // in rows; the launches take tiles
+    // L2 prefetch of a CTA's next pass-1 tile: on where measured to pay (n = 2^23); KOPEK_K3_PF1=0/1 forces it (tuning)
+    static const int pf_env = getenv("KOPEK_K3_PF1") && *getenv("KOPEK_K3_PF1") ? atoi(getenv("KOPEK_K3_PF1")) : -1;
+    const bool pf = pf_env >= 0 ? pf_env != 0 : n == (1ull << 23);
+    const float2 *pf_in = pf ? reinterpret_cast<const float2 *>(d_in) : nullptr;
     e = cudaErrorInvalidValue;
     switch (p.n1) {
-        case 256: e = launch_pass1<256>(p, in_map, mid, tb, keep, stream); break;
-        case 512: e = launch_pass1<512>(p, in_map, mid, tb, keep, stream); break;
-        case 1024: e = launch_pass1<1024>(p, in_map, mid, tb, keep, stream); break;
-        case 2048: e = launch_pass1<2048>(p, in_map, mid, tb, keep, stream); break;
-        case 4096: e = launch_pass1<4096>(p, in_map, mid, tb, keep, stream); break;
+        case 256: e = launch_pass1<256>(p, in_map, mid, tb, keep, stream, pf_in); break;
+        case 512: e = launch_pass1<512>(p, in_map, mid, tb, keep, stream, pf_in); break;
+        case 1024: e = launch_pass1<1024>(p, in_map, mid, tb, keep, stream, pf_in); break;
+        case 2048: e = launch_pass1<2048>(p, in_map, mid, tb, keep, stream, pf_in); break;
+        case 4096: e = launch_pass1<4096>(p, in_map, mid, tb, keep, stream, pf_in); break;
     }
     if (e != cudaSuccess) return fail(KOPEK_ERR_CUDA, "four-step pass 1 (N1=%d): %s", p.n1, cudaGetErrorString(e));
     float2 *o = reinterpret_cast<float2 *>(d_out);
