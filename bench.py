@@ -762,7 +762,7 @@ def bench_cfg3(c):
            "kernel": "k3_pass1<4096> + k3_pass2_r64 (TMA-staged tiles, two HBM passes)"}
     g = torch.Generator(device="cpu").manual_seed(7)
     sizes = {}
-    for lg in (20, 22, 24):
+    for lg in (20, 22, 23, 24):
         n = 1 << lg
         t = torch.arange(n, dtype=torch.float64)
         sig = (torch.sin(2 * math.pi * 0.01 * t) + 0.5 * torch.sin(2 * math.pi * 0.2503 * t)).to(torch.float32)
